@@ -1,0 +1,131 @@
+"""ctypes binding of libihmr_b200.so (the C ABI declared in include/ihmr_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing the import of any
+compute entry point raises, and every call checks the integer status the ABI returns.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libihmr_b200.so")
+
+EXPORTS = (
+    "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",
+    "ihmr_model_update_shapedirs", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
+    "ihmr_mano_backward", "ihmr_sdf_loss", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
+    "ihmr_opt_final", "ihmr_opt_value_and_grad",
+)
+
+P_CAM, P_TRANS, P_R_ORIENT, P_R_POSE, P_L_ORIENT, P_L_POSE, P_R_SHAPE, P_L_SHAPE = (1, 2, 4, 8, 16, 32, 64, 128)
+LOSS_IDS = {"joints_3d_loss_p": 0, "collision_loss": 1, "joints_2d_loss_p": 2}
+OPTIMIZERS = {"adam": 0, "sgd": 1}
+PARAM_MASKS = {
+    "pred_cam_params": P_CAM, "pred_hand_trans": P_TRANS, "pred_right_orient": P_R_ORIENT,
+    "pred_right_pose_params": P_R_POSE, "pred_left_orient": P_L_ORIENT,
+    "pred_left_pose_params": P_L_POSE, "pred_right_shape_params": P_R_SHAPE,
+    "pred_left_shape_params": P_L_SHAPE,
+}
+
+
+class Stage(C.Structure):
+    _fields_ = [
+        ("update_mask", C.c_uint32), ("lr", C.c_float), ("epoch", C.c_int32),
+        ("w_joints_2d", C.c_float), ("w_joints_3d", C.c_float), ("w_trans", C.c_float),
+        ("w_shape_reg", C.c_float), ("w_collision", C.c_float), ("w_finger_reg", C.c_float),
+        ("n_filters", C.c_int32), ("filter_loss", C.c_int32 * 4), ("filter_percent", C.c_float * 4),
+        ("select_loss", C.c_int32),
+    ]
+
+
+class Targets(C.Structure):
+    _fields_ = [
+        ("init_joints_2d", C.c_void_p), ("init_joints_3d", C.c_void_p), ("init_hand_trans_j", C.c_void_p),
+        ("gt_joints_3d", C.c_void_p), ("hand_type_array", C.c_void_p),
+    ]
+
+
+class IhmrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the library (once) and declares every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IhmrError(
+            f"{LIB_PATH} is missing. ihmr_b200 has no CPU or PyTorch fallback: build the CUDA "
+            "library first with `python -m ihmr_b200.build` (needs nvcc, targets sm_100a).")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    lib.ihmr_last_error.restype = C.c_char_p
+    lib.ihmr_last_error.argtypes = []
+    lib.ihmr_abi_version.restype = i32
+    lib.ihmr_abi_version.argtypes = []
+    lib.ihmr_model_create.restype = i32
+    lib.ihmr_model_create.argtypes = [vp] * 9 + [i32, C.POINTER(vp)]
+    lib.ihmr_model_destroy.restype = None
+    lib.ihmr_model_destroy.argtypes = [vp]
+    lib.ihmr_model_update_shapedirs.restype = i32
+    lib.ihmr_model_update_shapedirs.argtypes = [vp, vp, vp]
+    lib.ihmr_mano_workspace_bytes.restype = sz
+    lib.ihmr_mano_workspace_bytes.argtypes = [i32]
+    lib.ihmr_mano_forward.restype = i32
+    lib.ihmr_mano_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.ihmr_mano_backward.restype = i32
+    lib.ihmr_mano_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.ihmr_sdf_loss.restype = i32
+    lib.ihmr_sdf_loss.argtypes = [vp, i32, vp, vp, vp, vp, vp, f32, vp]
+    lib.ihmr_opt_workspace_bytes.restype = sz
+    lib.ihmr_opt_workspace_bytes.argtypes = [i32]
+    lib.ihmr_opt_stage.restype = i32
+    lib.ihmr_opt_stage.argtypes = [vp, i32, i32, vp, C.POINTER(Targets), C.POINTER(Stage), i32, i32, vp, sz, vp]
+    lib.ihmr_opt_final.restype = i32
+    lib.ihmr_opt_final.argtypes = [vp, i32, vp, C.POINTER(Targets), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.ihmr_opt_value_and_grad.restype = i32
+    lib.ihmr_opt_value_and_grad.argtypes = [vp, i32, i32, vp, C.POINTER(Targets), C.POINTER(Stage), vp, vp, vp, sz, vp]
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().ihmr_last_error().decode("utf-8", "replace")
+        raise IhmrError(f"{what} failed with status {status}: {msg}")
+
+
+def make_stage(stage: dict) -> Stage:
+    """Converts one strategy stage dict (src/strategies/opt_default.py layout) into the ABI struct."""
+    s = Stage()
+    mask = 0
+    for name in stage["update_params"]:
+        if name not in PARAM_MASKS:
+            raise IhmrError(f"unknown update_params entry {name!r}")
+        mask |= PARAM_MASKS[name]
+    lw = stage["loss_weights"]
+    s.update_mask, s.lr, s.epoch = mask, float(stage["lr"]), int(stage["epoch"])
+    s.w_joints_2d, s.w_joints_3d = float(lw["joints_2d_loss"]), float(lw["joints_3d_loss"])
+    s.w_trans, s.w_shape_reg = float(lw["trans_loss_weight"]), float(lw["shape_reg_loss_weight"])
+    s.w_collision, s.w_finger_reg = float(lw["collision_loss_weight"]), float(lw["finger_reg_loss_weight"])
+    filters = stage.get("filter_loss", [])
+    if len(filters) == 0:
+        raise AssertionError("filter_loss must not be empty")       # opt_utils.py:118
+    if len(filters) > 4:
+        raise IhmrError("at most 4 filter criteria are supported")
+    s.n_filters = len(filters)
+    for i, (name, crit) in enumerate(filters):
+        assert crit[0] in "+-"                                          # opt_utils.py:105
+        if name not in LOSS_IDS:
+            raise IhmrError(f"criterion {name!r} is not usable for filtering (opt_utils.py:57-67)")
+        s.filter_loss[i] = LOSS_IDS[name]
+        s.filter_percent[i] = float(crit)
+    if stage["select_loss"] not in LOSS_IDS:
+        raise IhmrError(f"criterion {stage['select_loss']!r} is not usable for selection")
+    s.select_loss = LOSS_IDS[stage["select_loss"]]
+    return s

@@ -1,0 +1,64 @@
+// Shared definitions for the ihmr_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ihmr_b200.h"
+
+namespace ihmr {
+
+constexpr int NV = IHMR_NUM_VERTS;        // 778
+constexpr int NF = IHMR_NUM_FACES;        // 1538
+constexpr int NJ = IHMR_NUM_JOINTS;       // 16
+constexpr int NB = IHMR_NUM_BETAS;        // 10
+constexpr int NPF = IHMR_NUM_POSE_FEAT;   // 135
+constexpr int NC = NV * 3;                // 2334 blend-shape columns
+constexpr int LDN = 2336;                 // padded column count / row stride of (hands x 2334) buffers
+constexpr int KP = 152;                   // blend rows: 135 pose features + 10 betas + 7 zero pad
+constexpr int PD = IHMR_PARAM_DIM;        // 122
+
+// offsets inside a (B,122) parameter row
+constexpr int P_CAM = 0, P_TRANS = 3, P_POSE = 6, P_SHAPE = 102;
+constexpr int P_R_ORIENT = 6, P_R_POSE = 9, P_L_ORIENT = 54, P_L_POSE = 57, P_R_SHAPE = 102, P_L_SHAPE = 112;
+
+void set_error(const char* fmt, ...);
+
+#define IHMR_CUDA_OK(expr)                                                              \
+    do {                                                                                \
+        cudaError_t e__ = (expr);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            ihmr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),    \
+                            __FILE__, __LINE__);                                        \
+            return IHMR_E_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define IHMR_LAUNCH_OK()                                                                \
+    do {                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess) {                                                       \
+            ihmr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__),\
+                            __FILE__, __LINE__);                                        \
+            return IHMR_E_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+}  // namespace ihmr
+
+// Device-resident constants of one hand model (all pointers are device memory).
+struct ihmr_model {
+    int device;
+    int num_sms;
+    float* D;        // (KP, LDN)  rows 0..134 posedirs, 135..144 shapedirs (k-major), rest 0
+    float* DT;       // (LDN, KP)  transpose of D
+    float* vtemp;    // (LDN)      v_template flattened, padded with 0
+    float* Jt;       // (48)       J_regressor @ v_template
+    float* Js;       // (10, 48)   J_regressor @ shapedirs[:, :, k]
+    float* Wt;       // (16, 778)  lbs weights, joint-major
+    float* W4;       // (4, 778, 4) lbs weights, tiles of 4 joints: W4[t][v][i] = W[v][4t+i]
+    float* hands_mean;  // (48) [0,0,0, hands_mean(45)]
+    float* Jreg;     // (16, 778)  kept for update_shapedirs
+    uint16_t* faces[2];  // (1538, 4) u16 per hand (right, left), 4th lane unused
+    int parents[16];
+};

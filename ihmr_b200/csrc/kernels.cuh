@@ -1,0 +1,70 @@
+// Host-side launchers shared between the C-ABI entry points (abi.cu) and the fused loop (opt.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ihmr {
+
+// Where a hand's (orient, pose, betas) come from.
+//   plain : three contiguous arrays (n,3) (n,45) (n,10)                      [MANO layer op]
+//   fused : rows of the (B,122) parameter matrix; hand h = 2*frame + side, the left hand
+//           (side 1) is mirrored: y,z of every axis-angle negated
+//           (src/models/optimize_model.py:180-188)                           [refinement loop]
+struct HandSrc {
+    const float* orient = nullptr;
+    const float* pose = nullptr;
+    const float* betas = nullptr;
+    const float* params = nullptr;
+};
+struct HandGrad {
+    float* orient = nullptr;
+    float* pose = nullptr;
+    float* betas = nullptr;
+    float* params_grad = nullptr;  // (B,122); pose/orient/shape slots are OVERWRITTEN
+};
+
+// Workspace carve-up for n hands (all fp32):
+struct ManoWs {
+    float* X;      // (n, KP)      blend coefficients [pose feature | betas | 0]
+    float* A;      // (n, 16, 12)  skinning transforms, 3x4 row-major
+    float* off;    // (n, LDN)     blend offsets  X @ D
+    float* gposed; // (n, LDN)     d loss / d v_posed
+    float* dA;     // (n, 16, 12)
+    float* dX;     // (n, KP)
+    float* joints; // (n, 16, 3)   scratch joints when the caller does not want them
+};
+size_t mano_ws_bytes(int n);
+ManoWs mano_ws_carve(void* base, int n);
+
+int launch_pose_prep(const ihmr_model* m, int n, HandSrc src, float* X, float* A, float* joints,
+                     cudaStream_t st);
+int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cudaStream_t st);
+int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts,
+                    cudaStream_t st);
+// gverts (n,778,3) may be null; gtips (n,5,3) may be null (extra gradient on the 5 fingertip vertices)
+int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
+                    const float* gtips, float* gposed, float* dA, cudaStream_t st);
+int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st);
+int launch_pose_bwd(const ihmr_model* m, int n, HandSrc src, const float* dA, const float* gjoints,
+                    const float* dX, HandGrad out, cudaStream_t st);
+
+// Interpenetration loss. verts (B,2,778,3). If `joints` and `params` are given the left hand is
+// stored in its mirrored model frame and is mapped to the world on load:
+//   v_world = diag(-1,1,1) v + shift,  shift = trans + J_R[0] - diag(-1,1,1) J_L[0]
+// (optimize_model.py:208-228); gradients are returned in the frame of the stored vertices and
+// their sum over the left hand (= d/d shift, world frame) goes to gshift (B,3).
+struct SdfArgs {
+    const float* verts = nullptr;
+    const float* joints = nullptr;     // (B,2,16,3) or null
+    const float* params = nullptr;     // (B,122) or null
+    const float* hand_type = nullptr;  // (B,2) or null: loss/grad masked unless both hands present
+    float* losses = nullptr;           // (B)
+    float* per_vert = nullptr;         // (B,1556) or null
+    float* origin = nullptr;           // (B,1556) or null
+    float* gverts = nullptr;           // (B,2,778,3) or null
+    float* gshift = nullptr;           // (B,3) or null
+    float grad_scale = 1.0f;           // gverts/gshift = grad_scale * d losses[b]/d(.)
+    float robustifier = 0.0f;
+};
+int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
+
+}  // namespace ihmr

@@ -1,0 +1,677 @@
+// MANO layer kernels: Rodrigues + kinematic chain per hand
+// (lane = joint), blend-shape contraction [pose feature | betas] x [posedirs ; shapedirs],
+// linear blend skinning over 778 vertices, and the analytic backward of each.
+//
+// Replaces smplx 0.1.28 MANO.forward -> lbs as called at
+// /root/reference/src/models/optimize_model.py:194-200, and its autograd backward.
+#include "kernels.cuh"
+
+namespace ihmr {
+
+// ------------------------------------------------------------------------------------ tree
+struct Tree {
+    int8_t parent[16];
+    int8_t depth[16];
+    int maxdepth;
+};
+
+static Tree make_tree(const int* parents) {
+    Tree t;
+    t.maxdepth = 0;
+    for (int j = 0; j < NJ; ++j) {
+        t.parent[j] = (int8_t)(parents[j] < 0 ? 0 : parents[j]);
+        t.depth[j] = (int8_t)(parents[j] < 0 ? 0 : t.depth[parents[j]] + 1);
+        if (t.depth[j] > t.maxdepth) t.maxdepth = t.depth[j];
+    }
+    return t;
+}
+
+// --------------------------------------------------------------------------- per-joint math
+struct JointState {
+    float r[3];     // axis-angle incl. hands_mean (and left-hand mirror in fused mode)
+    float theta;    // ||r + 1e-8||
+    float R[9];     // local rotation
+    float J[3];     // rest joint
+    float Jp[3];    // parent's rest joint (root: 0)
+    float Rgp[9];   // parent's global rotation (root: identity)
+    float Rg[9];    // global rotation
+    float tg[3];    // global translation = posed joint
+    float beta[NB];
+};
+
+__device__ __forceinline__ void mat3_mul(const float* a, const float* b, float* c) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            c[i * 3 + k] = a[i * 3 + 0] * b[0 * 3 + k] + a[i * 3 + 1] * b[1 * 3 + k] + a[i * 3 + 2] * b[2 * 3 + k];
+}
+
+// smplx.lbs.batch_rodrigues [UPSTREAM, M3]: angle = ||r + 1e-8||, n = r/angle,
+// R = I + sin K + (1-cos) K K
+__device__ __forceinline__ void rodrigues(const float* r, float& theta, float* R) {
+    const float e = 1e-8f;
+    float ax = r[0] + e, ay = r[1] + e, az = r[2] + e;
+    theta = sqrtf(ax * ax + ay * ay + az * az);
+    float nx = r[0] / theta, ny = r[1] / theta, nz = r[2] / theta;
+    float s, c;
+    sincosf(theta, &s, &c);
+    float b = 1.0f - c;
+    R[0] = 1.0f - b * (ny * ny + nz * nz);
+    R[1] = -s * nz + b * nx * ny;
+    R[2] = s * ny + b * nx * nz;
+    R[3] = s * nz + b * nx * ny;
+    R[4] = 1.0f - b * (nx * nx + nz * nz);
+    R[5] = -s * nx + b * ny * nz;
+    R[6] = -s * ny + b * nx * nz;
+    R[7] = s * nx + b * ny * nz;
+    R[8] = 1.0f - b * (nx * nx + ny * ny);
+}
+
+// d loss / d r given d loss / d R for the map above
+__device__ __forceinline__ void rodrigues_bwd(const float* r, float theta, const float* dR, float* dr) {
+    float nx = r[0] / theta, ny = r[1] / theta, nz = r[2] / theta;
+    float s, c;
+    sincosf(theta, &s, &c);
+    float b = 1.0f - c;
+    // K and K^2
+    float K[9] = {0.f, -nz, ny, nz, 0.f, -nx, -ny, nx, 0.f};
+    float K2[9] = {-(ny * ny + nz * nz), nx * ny, nx * nz, nx * ny, -(nx * nx + nz * nz), ny * nz,
+                   nx * nz, ny * nz, -(nx * nx + ny * ny)};
+    float da = 0.f, db = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        da += dR[i] * K[i];
+        db += dR[i] * K2[i];
+    }
+    // dK = s dR + b (dR K^T + K^T dR)
+    float dK[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.f;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) t += dR[i * 3 + m] * K[k * 3 + m] + K[m * 3 + i] * dR[m * 3 + k];
+            dK[i * 3 + k] = s * dR[i * 3 + k] + b * t;
+        }
+    float dn[3] = {dK[7] - dK[5], dK[2] - dK[6], dK[3] - dK[1]};
+    float dth = da * c + db * s;
+    float inv = 1.0f / theta;
+    float dot = dn[0] * r[0] + dn[1] * r[1] + dn[2] * r[2];
+    dth -= dot * inv * inv;
+    const float e = 1e-8f;
+    dr[0] = dn[0] * inv + dth * (r[0] + e) * inv;
+    dr[1] = dn[1] * inv + dth * (r[1] + e) * inv;
+    dr[2] = dn[2] * inv + dth * (r[2] + e) * inv;
+}
+
+// Loads joint j of hand h and runs Rodrigues + the kinematic chain with 16 lanes per hand.
+// All 32 lanes of the warp must call this (shuffles).
+template <bool FUSED>
+__device__ __forceinline__ void joint_forward(const HandSrc& src, int h, int j, int lane,
+                                              const float* __restrict__ hands_mean,
+                                              const float* __restrict__ Jt, const float* __restrict__ Js,
+                                              const Tree& tree, JointState& q) {
+    int side = 0;
+    if (FUSED) {
+        const float* row = src.params + (size_t)(h >> 1) * PD;
+        side = h & 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) q.r[c] = row[P_POSE + 48 * side + 3 * j + c];
+        if (side) { q.r[1] = -q.r[1]; q.r[2] = -q.r[2]; }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) q.beta[k] = row[P_SHAPE + NB * side + k];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            q.r[c] = (j == 0) ? src.orient[(size_t)h * 3 + c] : src.pose[(size_t)h * 45 + (j - 1) * 3 + c];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) q.beta[k] = src.betas[(size_t)h * NB + k];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) q.r[c] += hands_mean[j * 3 + c];   // M1 (entry 0..2 is zero)
+    rodrigues(q.r, q.theta, q.R);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float acc = Jt[j * 3 + c];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc += Js[k * 48 + j * 3 + c] * q.beta[k];
+        q.J[c] = acc;
+    }
+    // chain, level by level (parents have smaller depth)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { q.Rg[i] = q.R[i]; q.Rgp[i] = (i % 4 == 0) ? 1.f : 0.f; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { q.tg[c] = q.J[c]; q.Jp[c] = 0.f; }
+    const int base = lane & 16;
+    const int p = tree.parent[j];
+    const int dep = tree.depth[j];
+    for (int level = 1; level <= tree.maxdepth; ++level) {
+        float pr[9], pt[3], pj[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) pr[i] = __shfl_sync(0xffffffffu, q.Rg[i], base + p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            pt[c] = __shfl_sync(0xffffffffu, q.tg[c], base + p);
+            pj[c] = __shfl_sync(0xffffffffu, q.J[c], base + p);
+        }
+        if (dep == level) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) q.Rgp[i] = pr[i];
+            mat3_mul(pr, q.R, q.Rg);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) q.Jp[c] = pj[c];
+            float d[3] = {q.J[0] - pj[0], q.J[1] - pj[1], q.J[2] - pj[2]};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) q.tg[c] = pr[c * 3 + 0] * d[0] + pr[c * 3 + 1] * d[1] + pr[c * 3 + 2] * d[2] + pt[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- pose prep
+template <bool FUSED>
+__global__ void __launch_bounds__(128) k_pose_prep(int n, HandSrc src, const float* __restrict__ hands_mean,
+                                                  const float* __restrict__ Jt, const float* __restrict__ Js,
+                                                  Tree tree, float* __restrict__ X, float* __restrict__ A,
+                                                  float* __restrict__ joints) {
+    const int lane = threadIdx.x & 31, j = lane & 15;
+    int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool active = h < n;
+    if (!active) h = n - 1;
+    JointState q;
+    joint_forward<FUSED>(src, h, j, lane, hands_mean, Jt, Js, tree, q);
+    if (!active) return;
+    float* xr = X + (size_t)h * KP;
+    if (j >= 1) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) xr[(j - 1) * 9 + i] = q.R[i] - ((i % 4 == 0) ? 1.f : 0.f);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) xr[NPF + k] = q.beta[k];
+#pragma unroll
+        for (int k = NPF + NB; k < KP; ++k) xr[k] = 0.f;
+    }
+    float4* a = reinterpret_cast<float4*>(A + ((size_t)h * NJ + j) * 12);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float ta = q.tg[r] - (q.Rg[r * 3 + 0] * q.J[0] + q.Rg[r * 3 + 1] * q.J[1] + q.Rg[r * 3 + 2] * q.J[2]);
+        a[r] = make_float4(q.Rg[r * 3 + 0], q.Rg[r * 3 + 1], q.Rg[r * 3 + 2], ta);
+    }
+    if (joints) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) joints[((size_t)h * NJ + j) * 3 + c] = q.tg[c];
+    }
+}
+
+// ---------------------------------------------------------------------------- pose backward
+template <bool FUSED>
+__global__ void __launch_bounds__(128) k_pose_bwd(int n, HandSrc src, const float* __restrict__ hands_mean,
+                                                 const float* __restrict__ Jt, const float* __restrict__ Js,
+                                                 Tree tree, const float* __restrict__ dA,
+                                                 const float* __restrict__ gjoints,
+                                                 const float* __restrict__ dX, HandGrad out) {
+    const int lane = threadIdx.x & 31, j = lane & 15, base = lane & 16;
+    int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool active = h < n;
+    if (!active) h = n - 1;
+    JointState q;
+    joint_forward<FUSED>(src, h, j, lane, hands_mean, Jt, Js, tree, q);
+
+    // seeds from the skinning transforms A_j = [Rg | tg - Rg J] and the posed joints
+    float dRg[9], dtg[3], dJ[3];
+    {
+        const float4* a = reinterpret_cast<const float4*>(dA + ((size_t)h * NJ + j) * 12);
+        float dta[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float4 v = a[r];
+            dRg[r * 3 + 0] = v.x; dRg[r * 3 + 1] = v.y; dRg[r * 3 + 2] = v.z; dta[r] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            dtg[r] = dta[r] + (gjoints ? gjoints[((size_t)h * NJ + j) * 3 + r] : 0.f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dRg[r * 3 + c] -= dta[r] * q.J[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            dJ[c] = -(q.Rg[0 * 3 + c] * dta[0] + q.Rg[1 * 3 + c] * dta[1] + q.Rg[2 * 3 + c] * dta[2]);
+    }
+    // reverse chain: deepest level first; a parent gathers its children in ascending joint order
+    float dR[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dR[i] = dRg[i];   // root: Rg = R
+    const int dep = tree.depth[j];
+    for (int level = tree.maxdepth; level >= 1; --level) {
+        float c[15];
+        if (dep == level) {
+            // dRg_parent += dRg R^T + dtg (J - Jp)^T ; dtg_parent += dtg ; dJ_parent -= Rgp^T dtg
+            float d[3] = {q.J[0] - q.Jp[0], q.J[1] - q.Jp[1], q.J[2] - q.Jp[2]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    c[r * 3 + k] = dRg[r * 3 + 0] * q.R[k * 3 + 0] + dRg[r * 3 + 1] * q.R[k * 3 + 1] +
+                                   dRg[r * 3 + 2] * q.R[k * 3 + 2] + dtg[r] * d[k];
+            float rt[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                rt[k] = q.Rgp[0 * 3 + k] * dtg[0] + q.Rgp[1 * 3 + k] * dtg[1] + q.Rgp[2 * 3 + k] * dtg[2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c[9 + k] = dtg[k]; c[12 + k] = -rt[k]; dJ[k] += rt[k]; }
+            // local rotation gradient: dR = Rgp^T dRg
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    dR[r * 3 + k] = q.Rgp[0 * 3 + r] * dRg[0 * 3 + k] + q.Rgp[1 * 3 + r] * dRg[1 * 3 + k] +
+                                    q.Rgp[2 * 3 + r] * dRg[2 * 3 + k];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 15; ++i) c[i] = 0.f;
+        }
+        for (int ch = 1; ch < NJ; ++ch) {
+            const bool mine = (tree.parent[ch] == j) && (tree.depth[ch] == level);
+#pragma unroll
+            for (int i = 0; i < 15; ++i) {
+                float v = __shfl_sync(0xffffffffu, c[i], base + ch);
+                if (mine) {
+                    if (i < 9) dRg[i] += v;
+                    else if (i < 12) dtg[i - 9] += v;
+                    else dJ[i - 12] += v;
+                }
+            }
+        }
+    }
+    if (dep == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dR[i] = dRg[i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dJ[k] += dtg[k];
+    }
+    // pose-feature gradient from the blend GEMM: f = vec(R_j - I), j >= 1
+    const float* dx = dX + (size_t)h * KP;
+    if (j >= 1) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dR[i] += dx[(j - 1) * 9 + i];
+    }
+    float dr[3];
+    rodrigues_bwd(q.r, q.theta, dR, dr);
+    // d beta = Js^T dJ summed over the 16 joints (fixed butterfly order) + the blend-GEMM part
+    float db[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        float v = Js[k * 48 + j * 3 + 0] * dJ[0] + Js[k * 48 + j * 3 + 1] * dJ[1] + Js[k * 48 + j * 3 + 2] * dJ[2];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        db[k] = v + dx[NPF + k];
+    }
+    if (!active) return;
+    if (FUSED) {
+        const int side = h & 1;
+        float* g = out.params_grad + (size_t)(h >> 1) * PD;
+        if (side) { dr[1] = -dr[1]; dr[2] = -dr[2]; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[P_POSE + 48 * side + 3 * j + c] += dr[c];
+        if (j == 0) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) g[P_SHAPE + NB * side + k] += db[k];
+        }
+    } else {
+        if (j == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out.orient[(size_t)h * 3 + c] = dr[c];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) out.betas[(size_t)h * NB + k] = db[k];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out.pose[(size_t)h * 45 + (j - 1) * 3 + c] = dr[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- SIMT SGEMM
+// C[M,N] = A[M,K] B[K,N], row-major, K % BK == 0, N % 4 == 0, lda/ldb/ldc % 4 == 0.
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+        float* __restrict__ C, int ldc) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int k = 0; k < TN; ++k) acc[i][k] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // A tile: BM rows x BK cols, float4 along K
+        for (int i = tid; i < BM * (BK / 4); i += NT) {
+            int r = i / (BK / 4), c4 = i % (BK / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < M) v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + c4 * 4);
+            As[c4 * 4 + 0][r] = v.x; As[c4 * 4 + 1][r] = v.y; As[c4 * 4 + 2][r] = v.z; As[c4 * 4 + 3][r] = v.w;
+        }
+        for (int i = tid; i < BK * (BN / 4); i += NT) {
+            int r = i / (BN / 4), c4 = i % (BN / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + c4 * 4 < N) v = *reinterpret_cast<const float4*>(B + (size_t)(k0 + r) * ldb + n0 + c4 * 4);
+            *reinterpret_cast<float4*>(&Bs[r][c4 * 4]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int k = 0; k < TN; ++k) b[k] = Bs[kk][tx + k * (BN / TN)];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int k = 0; k < TN; ++k) acc[i][k] += a[i] * b[k];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int r = m0 + ty * TM + i;
+        if (r >= M) continue;
+#pragma unroll
+        for (int k = 0; k < TN; ++k) {
+            int c = n0 + tx + k * (BN / TN);
+            if (c < N) C[(size_t)r * ldc + c] = acc[i][k];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- skinning
+constexpr int SK_THREADS = 416;   // 13 warps x 2 vertex slots = 832 >= 778
+constexpr int SK_SLOTS = 2;
+constexpr int SK_HPC = 8;         // hands per CTA
+
+__global__ void __launch_bounds__(SK_THREADS)
+k_skin_fwd(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
+           const float* __restrict__ Wt, float* __restrict__ verts) {
+    __shared__ float4 sA[SK_HPC][48];
+    const int tid = threadIdx.x;
+    const int h0 = blockIdx.x * SK_HPC;
+    const int nh = min(SK_HPC, n - h0);
+    float w[SK_SLOTS][NJ], vt[SK_SLOTS][3];
+    int v[SK_SLOTS];
+#pragma unroll
+    for (int s = 0; s < SK_SLOTS; ++s) {
+        v[s] = tid + s * SK_THREADS;
+        const bool ok = v[s] < NV;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) w[s][j] = ok ? Wt[j * NV + v[s]] : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vt[s][c] = ok ? vtemp[v[s] * 3 + c] : 0.f;
+    }
+    const float4* A4 = reinterpret_cast<const float4*>(A) + (size_t)h0 * 48;
+    for (int i = tid; i < nh * 48; i += SK_THREADS) sA[i / 48][i % 48] = A4[i];
+    __syncthreads();
+    for (int hh = 0; hh < nh; ++hh) {
+        const size_t h = h0 + hh;
+        float vp[SK_SLOTS][3], T[SK_SLOTS][12];
+#pragma unroll
+        for (int s = 0; s < SK_SLOTS; ++s) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) vp[s][c] = (v[s] < NV) ? vt[s][c] + off[h * LDN + v[s] * 3 + c] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) T[s][i] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            float4 r0 = sA[hh][j * 3 + 0], r1 = sA[hh][j * 3 + 1], r2 = sA[hh][j * 3 + 2];
+#pragma unroll
+            for (int s = 0; s < SK_SLOTS; ++s) {
+                const float ww = w[s][j];
+                T[s][0] += ww * r0.x; T[s][1] += ww * r0.y; T[s][2] += ww * r0.z; T[s][3] += ww * r0.w;
+                T[s][4] += ww * r1.x; T[s][5] += ww * r1.y; T[s][6] += ww * r1.z; T[s][7] += ww * r1.w;
+                T[s][8] += ww * r2.x; T[s][9] += ww * r2.y; T[s][10] += ww * r2.z; T[s][11] += ww * r2.w;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SK_SLOTS; ++s) {
+            if (v[s] < NV) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    verts[(h * NV + v[s]) * 3 + r] =
+                        T[s][r * 4 + 0] * vp[s][0] + T[s][r * 4 + 1] * vp[s][1] + T[s][r * 4 + 2] * vp[s][2] + T[s][r * 4 + 3];
+            }
+        }
+    }
+}
+
+// Reduce-scatter of 48 per-lane partial sums over the 32 lanes of a warp (fixed order).
+// Afterwards acc[0..2] of every lane holds the warp totals of elements seg..seg+2 where
+// seg = 24*b4 + 12*b3 + 6*b2 + 3*b1 (b_i = bit i of the lane id).
+__device__ __forceinline__ void warp_reduce_scatter_48(float (&acc)[48], int lane) {
+#define IHMR_RS_STAGE(OFF, HALF)                                              \
+    {                                                                         \
+        const bool up = (lane & OFF) != 0;                                    \
+        _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                    \
+            float send = up ? acc[i] : acc[i + HALF];                         \
+            float keep = up ? acc[i + HALF] : acc[i];                         \
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);          \
+        }                                                                     \
+    }
+    IHMR_RS_STAGE(16, 24)
+    IHMR_RS_STAGE(8, 12)
+    IHMR_RS_STAGE(4, 6)
+    IHMR_RS_STAGE(2, 3)
+#undef IHMR_RS_STAGE
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+}
+
+constexpr int SKB_THREADS = 384;        // 12 warps = 4 joint tiles x 3 vertex slices
+constexpr int SKB_KSLICES = 3;
+constexpr int SKB_SLICE = 288;          // vertices per slice (9 x 32)
+
+__global__ void __launch_bounds__(SKB_THREADS)
+k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
+           const float* __restrict__ W4, const float* __restrict__ gverts, const float* __restrict__ gtips,
+           float* __restrict__ gposed, float* __restrict__ dA) {
+    extern __shared__ float4 smem4[];
+    float4* sW4 = smem4;                       // [4][778]
+    float4* sG = sW4 + 4 * NV;                 // [778]  (g, 0)
+    float4* sP = sG + NV;                      // [778]  (v_posed, 1)
+    float4* sA = sP + NV;                      // [SK_HPC][48]
+    float* sPart = reinterpret_cast<float*>(sA + SK_HPC * 48);   // [SKB_KSLICES][192]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h0 = blockIdx.x * SK_HPC;
+    const int nh = min(SK_HPC, n - h0);
+
+    const float4* W4g = reinterpret_cast<const float4*>(W4);
+    for (int i = tid; i < 4 * NV; i += SKB_THREADS) sW4[i] = W4g[i];
+    const float4* A4 = reinterpret_cast<const float4*>(A) + (size_t)h0 * 48;
+    for (int i = tid; i < nh * 48; i += SKB_THREADS) sA[i] = A4[i];
+    __syncthreads();
+
+    for (int hh = 0; hh < nh; ++hh) {
+        const size_t h = h0 + hh;
+        // phase A (thread = vertex): d v_posed = T^T g, stash (g,0) and (v_posed,1)
+        for (int v = tid; v < NV; v += SKB_THREADS) {
+            float g[3] = {0.f, 0.f, 0.f}, vp[3];
+            if (gverts) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[c] = gverts[(h * NV + v) * 3 + c];
+            }
+            if (gtips) {
+                const int tip = (v == 744) ? 0 : (v == 320) ? 1 : (v == 443) ? 2 : (v == 554) ? 3 : (v == 671) ? 4 : -1;
+                if (tip >= 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) g[c] += gtips[(h * 5 + tip) * 3 + c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) vp[c] = vtemp[v * 3 + c] + off[h * LDN + v * 3 + c];
+            float T[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) T[i] = 0.f;
+#pragma unroll
+            for (int jt = 0; jt < 4; ++jt) {
+                const float4 w4 = sW4[jt * NV + v];
+                const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int ji = 0; ji < 4; ++ji) {
+                    const int j = jt * 4 + ji;
+                    const float4 r0 = sA[hh * 48 + j * 3 + 0], r1 = sA[hh * 48 + j * 3 + 1], r2 = sA[hh * 48 + j * 3 + 2];
+                    const float ww = wj[ji];
+                    T[0] += ww * r0.x; T[1] += ww * r0.y; T[2] += ww * r0.z;
+                    T[3] += ww * r1.x; T[4] += ww * r1.y; T[5] += ww * r1.z;
+                    T[6] += ww * r2.x; T[7] += ww * r2.y; T[8] += ww * r2.z;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                gposed[h * LDN + v * 3 + c] = T[0 * 3 + c] * g[0] + T[1 * 3 + c] * g[1] + T[2 * 3 + c] * g[2];
+            sG[v] = make_float4(g[0], g[1], g[2], 0.f);
+            sP[v] = make_float4(vp[0], vp[1], vp[2], 1.f);
+        }
+        if (tid < LDN - NC) gposed[h * LDN + NC + tid] = 0.f;   // zero the pad columns (GEMM reads them)
+        __syncthreads();
+        // phase B (warp = joint tile x vertex slice): dA_j += W[v,j] g_v (x) [v_posed, 1]
+        {
+            const int t = warp & 3, ks = warp >> 2;
+            float acc[48];
+#pragma unroll
+            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+            const int vend = min(NV, (ks + 1) * SKB_SLICE);
+            for (int vv = ks * SKB_SLICE + lane; vv < vend; vv += 32) {
+                const float4 w4 = sW4[t * NV + vv], g = sG[vv], p = sP[vv];
+                const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+                const float gg[3] = {g.x, g.y, g.z};
+                const float pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float wg = wj[i] * gg[r];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[i * 12 + r * 4 + c] += wg * pp[c];
+                    }
+            }
+            warp_reduce_scatter_48(acc, lane);
+            if ((lane & 1) == 0) {
+                const int seg = ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + ((lane >> 1) & 1) * 3;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) sPart[ks * 192 + t * 48 + seg + i] = acc[i];
+            }
+        }
+        __syncthreads();
+        if (tid < 192) {
+            float s = sPart[tid];
+#pragma unroll
+            for (int ks = 1; ks < SKB_KSLICES; ++ks) s += sPart[ks * 192 + tid];
+            dA[h * 192 + tid] = s;
+        }
+        // the next hand's phase A only touches sG/sP (all phase-B readers are past the barrier
+        // above); its phase-B writes to sPart come after its own first barrier, i.e. after the
+        // reads just above in program order of those threads and a barrier for the others.
+    }
+}
+
+constexpr size_t SKIN_BWD_SMEM = sizeof(float4) * (4 * NV + 2 * NV + SK_HPC * 48) + sizeof(float) * SKB_KSLICES * 192;
+
+// -------------------------------------------------------------------------------- launchers
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t mano_ws_bytes(int n) {
+    size_t b = 0;
+    b += align_up((size_t)n * KP * 4, 256);          // X
+    b += align_up((size_t)n * 192 * 4, 256);         // A
+    b += align_up((size_t)n * LDN * 4, 256);         // off
+    b += align_up((size_t)n * LDN * 4, 256);         // gposed
+    b += align_up((size_t)n * 192 * 4, 256);         // dA
+    b += align_up((size_t)n * KP * 4, 256);          // dX
+    b += align_up((size_t)n * 48 * 4, 256);          // joints
+    return b;
+}
+
+ManoWs mano_ws_carve(void* base, int n) {
+    ManoWs w;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t bytes) { float* r = reinterpret_cast<float*>(p); p += align_up(bytes, 256); return r; };
+    w.X = take((size_t)n * KP * 4);
+    w.A = take((size_t)n * 192 * 4);
+    w.off = take((size_t)n * LDN * 4);
+    w.gposed = take((size_t)n * LDN * 4);
+    w.dA = take((size_t)n * 192 * 4);
+    w.dX = take((size_t)n * KP * 4);
+    w.joints = take((size_t)n * 48 * 4);
+    return w;
+}
+
+int launch_pose_prep(const ihmr_model* m, int n, HandSrc src, float* X, float* A, float* joints, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    Tree tree = make_tree(m->parents);
+    dim3 grid((n * 16 + 127) / 128);
+    if (src.params)
+        k_pose_prep<true><<<grid, 128, 0, st>>>(n, src, m->hands_mean, m->Jt, m->Js, tree, X, A, joints);
+    else
+        k_pose_prep<false><<<grid, 128, 0, st>>>(n, src, m->hands_mean, m->Jt, m->Js, tree, X, A, joints);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    dim3 grid((LDN + 127) / 128, (n + 127) / 128);
+    k_sgemm<128, 128, 8, 8, 8><<<grid, 256, 0, st>>>(n, LDN, KP, X, KP, m->D, LDN, off, LDN);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    dim3 grid(1, (n + 63) / 64);
+    k_sgemm<64, 160, 8, 8, 5><<<grid, 256, 0, st>>>(n, KP, LDN, gposed, LDN, m->DT, KP, dX, KP);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    k_skin_fwd<<<(n + SK_HPC - 1) / SK_HPC, SK_THREADS, 0, st>>>(n, off, A, m->vtemp, m->Wt, verts);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
+                    const float* gtips, float* gposed, float* dA, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    static bool configured = false;   // idempotent attribute; a race only repeats the same call
+    if (!configured) {
+        IHMR_CUDA_OK(cudaFuncSetAttribute(k_skin_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_BWD_SMEM));
+        configured = true;
+    }
+    k_skin_bwd<<<(n + SK_HPC - 1) / SK_HPC, SKB_THREADS, SKIN_BWD_SMEM, st>>>(n, off, A, m->vtemp, m->W4,
+                                                                           gverts, gtips, gposed, dA);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_pose_bwd(const ihmr_model* m, int n, HandSrc src, const float* dA, const float* gjoints,
+                    const float* dX, HandGrad out, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    Tree tree = make_tree(m->parents);
+    dim3 grid((n * 16 + 127) / 128);
+    if (src.params)
+        k_pose_bwd<true><<<grid, 128, 0, st>>>(n, src, m->hands_mean, m->Jt, m->Js, tree, dA, gjoints, dX, out);
+    else
+        k_pose_bwd<false><<<grid, 128, 0, st>>>(n, src, m->hands_mean, m->Jt, m->Js, tree, dA, gjoints, dX, out);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+}  // namespace ihmr

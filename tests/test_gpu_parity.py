@@ -1,0 +1,250 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances are the ones BASELINE.json's north_star states: max vertex error <= 1e-5 m per MANO
+forward, loss and gradient relative error <= 1e-4, final refined joints within 0.1 mm.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+VERT_TOL = 1e-5        # metres
+REL_TOL = 1e-4
+JOINT_TOL = 1e-4       # metres (0.1 mm)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def cuda_layers(model_root):
+    from ihmr_b200 import mano_layer
+    right = mano_layer.create(os.path.join(model_root, "MANO_RIGHT.pkl"), "mano", use_pca=False, is_rhand=True).cuda()
+    left = mano_layer.create(os.path.join(model_root, "MANO_LEFT.pkl"), "mano", use_pca=False, is_rhand=False).cuda()
+    return right, left
+
+
+@pytest.fixture(scope="module")
+def oracle64(oracle_layers):
+    r, l = copy.deepcopy(oracle_layers[0]).double(), copy.deepcopy(oracle_layers[1]).double()
+    return r, l
+
+
+def random_hands(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    orient = (torch.rand(n, 3, generator=g) - 0.5) * 3.0
+    pose = torch.randn(n, 45, generator=g) * 0.4
+    betas = torch.randn(n, 10, generator=g)
+    orient[0] = 0
+    pose[0] = 0
+    return orient, pose, betas
+
+
+# ------------------------------------------------------------------------------ MANO layer
+def test_mano_forward_golden(cuda_layers):
+    z = np.load(os.path.join(H.GOLDEN, "leaves.npz"))
+    out = cuda_layers[0](global_orient=torch.tensor(z["mano_orient"]).cuda(), hand_pose=torch.tensor(z["mano_pose"]).cuda(),
+                         betas=torch.tensor(z["mano_betas"]).cuda())
+    assert np.abs(out.vertices.cpu().numpy() - z["mano_vertices"]).max() <= VERT_TOL
+    assert np.abs(out.joints.cpu().numpy() - z["mano_joints"]).max() <= VERT_TOL
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 333])
+def test_mano_forward_vs_oracle(cuda_layers, oracle64, n):
+    orient, pose, betas = random_hands(n, seed=n)
+    ref = oracle64[0](global_orient=orient.double(), hand_pose=pose.double(), betas=betas.double())
+    out = cuda_layers[0](global_orient=orient.cuda(), hand_pose=pose.cuda(), betas=betas.cuda())
+    assert out.vertices.shape == (n, 778, 3) and out.joints.shape == (n, 16, 3)
+    assert (out.vertices.cpu().double() - ref.vertices).abs().max().item() <= VERT_TOL
+    assert (out.joints.cpu().double() - ref.joints).abs().max().item() <= VERT_TOL
+
+
+@pytest.mark.parametrize("n", [1, 9, 40])
+def test_mano_backward_vs_oracle(cuda_layers, oracle64, n):
+    orient, pose, betas = random_hands(n, seed=100 + n)
+    g = torch.Generator().manual_seed(5)
+    gv, gj = torch.randn(n, 778, 3, generator=g), torch.randn(n, 16, 3, generator=g) * 10
+    ins64 = [t.double().requires_grad_(True) for t in (orient, pose, betas)]
+    ref = oracle64[0](global_orient=ins64[0], hand_pose=ins64[1], betas=ins64[2])
+    ((ref.vertices * gv.double()).sum() + (ref.joints * gj.double()).sum()).backward()
+    ins = [t.cuda().requires_grad_(True) for t in (orient, pose, betas)]
+    out = cuda_layers[0](global_orient=ins[0], hand_pose=ins[1], betas=ins[2])
+    ((out.vertices * gv.cuda()).sum() + (out.joints * gj.cuda()).sum()).backward()
+    for a, b, name in zip(ins, ins64, ("orient", "pose", "betas")):
+        assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) <= REL_TOL, name
+
+
+def test_mano_backward_only_vertices_or_joints(cuda_layers, oracle64):
+    orient, pose, betas = random_hands(5, seed=9)
+    for use in ("vertices", "joints"):
+        ins64 = [t.double().requires_grad_(True) for t in (orient, pose, betas)]
+        getattr(oracle64[0](global_orient=ins64[0], hand_pose=ins64[1], betas=ins64[2]), use).square().sum().backward()
+        ins = [t.cuda().requires_grad_(True) for t in (orient, pose, betas)]
+        getattr(cuda_layers[0](global_orient=ins[0], hand_pose=ins[1], betas=ins[2]), use).square().sum().backward()
+        for a, b in zip(ins, ins64):
+            assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) <= REL_TOL
+
+
+# ---------------------------------------------------------------------- penetration loss
+def _cuda_sdf(cuda_layers):
+    from ihmr_b200 import sdf_loss
+    return sdf_loss.SDFLoss(cuda_layers[0].faces, cuda_layers[1].faces).cuda()
+
+
+def test_sdf_golden(cuda_layers):
+    z = np.load(os.path.join(H.GOLDEN, "leaves.npz"))
+    hv = torch.tensor(z["sdf_hand_verts"]).cuda().requires_grad_(True)
+    losses, per_vert, origin = _cuda_sdf(cuda_layers)(hv, return_per_vert_loss=True, return_origin_scale_loss=True)
+    losses.sum().backward()
+    assert rel_err(losses.detach().cpu().numpy(), z["sdf_losses"]) <= REL_TOL
+    assert np.abs(origin.cpu().numpy() - z["sdf_origin_scale"]).max() <= 1e-6
+    assert rel_err(hv.grad.cpu().numpy(), z["sdf_grad"]) <= REL_TOL
+
+
+@pytest.mark.parametrize("mode,start,count", [("typical", 0, 6), ("collision", 0, 3), ("typical", 40, 6)])
+def test_sdf_vs_oracle(cuda_layers, oracle_layers, mode, start, count):
+    from ihmr_b200 import synthetic
+    from oracle import mano_oracle, sdf_oracle
+    raw = synthetic.make_raw_frames(start, count, seed=0, mode=mode)
+    with torch.no_grad():
+        rv, lv, _ = mano_oracle.two_hand_forward(oracle_layers[0], torch.tensor(raw["true_pose"]),
+                                                 torch.tensor(raw["true_shape"]), torch.tensor(raw["true_trans"]))
+    hv_cpu = torch.stack([rv, lv], 1).clone().requires_grad_(True)
+    ref = sdf_oracle.SDFLoss(oracle_layers[0].faces, oracle_layers[1].faces)
+    l_ref, pv_ref, o_ref = ref(hv_cpu, True, True)
+    l_ref.sum().backward()
+    hv = hv_cpu.detach().cuda().requires_grad_(True)
+    l, pv, o = _cuda_sdf(cuda_layers)(hv, return_per_vert_loss=True, return_origin_scale_loss=True)
+    l.sum().backward()
+    assert o.shape == (count, 1556)
+    scale = max(float(l_ref.abs().max()), 1e-12)
+    assert float((l.detach().cpu() - l_ref.detach()).abs().max()) <= REL_TOL * scale + 1e-9
+    assert float((o.cpu() - o_ref).abs().max()) <= 2e-6
+    assert float((pv.cpu() - pv_ref.detach()).abs().max()) <= 2e-5
+    gscale = max(float(hv_cpu.grad.abs().max()), 1e-12)
+    assert float((hv.grad.cpu() - hv_cpu.grad).abs().max()) <= REL_TOL * gscale + 1e-9
+
+
+def test_sdf_disjoint_hands_is_exact_zero(cuda_layers):
+    orient, pose, betas = random_hands(4, seed=3)
+    v = cuda_layers[0](global_orient=orient.cuda(), hand_pose=pose.cuda(), betas=betas.cuda()).vertices
+    hv = torch.stack([v[:2], v[2:] + 5.0], 1).contiguous().requires_grad_(True)
+    l, pv, o = _cuda_sdf(cuda_layers)(hv, return_per_vert_loss=True, return_origin_scale_loss=True)
+    l.sum().backward()
+    assert float(l.abs().max()) == 0.0 and float(o.abs().max()) == 0.0 and float(hv.grad.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ one fused iteration
+STAGE_IDS = [0, 1, 2, 3]
+
+
+@pytest.mark.parametrize("stage_id", STAGE_IDS)
+@pytest.mark.parametrize("mode", ["typical", "collision"])
+def test_value_and_grad_vs_oracle(model_root, oracle_layers, stage_id, mode):
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default
+    B = 3
+    data = H.make_batch(oracle_layers[0], 0, B, mode=mode)
+    batch = H.torch_batch(data)
+    stage = opt_default[stage_id]
+    # oracle: the host loop restatement with autograd over the oracle leaves, all params live
+    hl = H.oracle_loop(oracle_layers, B, 1, 1)
+    hl.set_input(batch)
+    hl.init_optimize()
+    for k in hl.p:
+        hl.p[k] = hl.p[k].detach().clone().requires_grad_(True)
+    hl.forward()
+    hl.compute_loss(stage["loss_weights"])
+    hl.loss.backward()
+    ref_losses = [hl.joints_2d_loss_p, hl.joints_3d_loss_p, hl.hand_trans_loss_p, hl.collision_loss,
+                  hl.shape_reg_loss, hl.finger_reg_loss]
+    ref_grad = torch.cat([torch.zeros(B, 3), hl.p["pred_hand_trans"].grad.view(B, 3), hl.p["pred_right_orient"].grad,
+                          hl.p["pred_right_pose_params"].grad, hl.p["pred_left_orient"].grad,
+                          hl.p["pred_left_pose_params"].grad, hl.p["pred_right_shape_params"].grad,
+                          hl.p["pred_left_shape_params"].grad], 1).numpy()
+
+    model = OptimizeModel(H.make_opt(model_root, B))
+    model.set_input(batch)
+    model.init_optimize()
+    losses, grad = model.value_and_grad(stage)
+    losses, grad = losses.cpu().numpy(), grad.cpu().numpy()
+    for i, r in enumerate(ref_losses):
+        r = float(r)
+        assert abs(losses[i] - r) <= REL_TOL * max(abs(r), 1e-6), (i, losses[i], r)
+    groups = {"trans": slice(3, 6), "r_orient": slice(6, 9), "r_pose": slice(9, 54), "l_orient": slice(54, 57),
+              "l_pose": slice(57, 102), "r_shape": slice(102, 112), "l_shape": slice(112, 122)}
+    for name, sl in groups.items():
+        assert rel_err(grad[:, sl], ref_grad[:, sl]) <= REL_TOL, name
+
+
+# ------------------------------------------------------------------------- whole loop
+@pytest.mark.parametrize("fixture", ["loop_b2_short.npz", "loop_collision_short.npz", "loop_cfg1.npz"])
+def test_full_loop_vs_golden(model_root, fixture):
+    """The fixtures were produced by the UNMODIFIED reference host loop + oracle leaves."""
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default, with_epochs
+    data, out, epochs, freq = H.load_golden(fixture)
+    B = data["init_cam"].shape[0]
+    opt = H.make_opt(model_root, B, save_mid_freq=freq, strategy=with_epochs(opt_default, epochs))
+    model = OptimizeModel(opt)
+    model.set_input(H.torch_batch(data))
+    model.init_optimize()
+    model.optimize(0, 1)
+    res = model.get_pred_result()
+    assert list(res.keys()) == list(out.keys())
+    for k in out:
+        assert res[k].shape == out[k].shape and res[k].dtype == out[k].dtype, k
+    assert np.abs(res["pred_joints_3d"] - out["pred_joints_3d"]).max() <= JOINT_TOL
+    assert np.abs(res["pred_right_hand_verts"] - out["pred_right_hand_verts"]).max() <= JOINT_TOL
+    assert np.abs(res["pred_left_hand_verts"] - out["pred_left_hand_verts"]).max() <= JOINT_TOL
+    assert np.abs(res["pred_hand_trans"] - out["pred_hand_trans"]).max() <= JOINT_TOL
+    assert np.abs(res["collision_loss_origin_scale"] - out["collision_loss_origin_scale"]).max() <= JOINT_TOL
+    assert np.abs(res["pred_pose_params"] - out["pred_pose_params"]).max() <= 2e-3
+    assert np.abs(res["pred_shape_params"] - out["pred_shape_params"]).max() <= 2e-3
+
+
+def test_dropin_leaves_under_host_loop(model_root, oracle_layers, cuda_layers):
+    """L0 boundary: the same host loop drives (i) oracle leaves on CPU and (ii) the CUDA leaves."""
+    from ihmr_b200 import sdf_loss
+    from oracle import host_loop_oracle as HL
+    B, epochs, freq = 2, 2, 1
+    batch = H.torch_batch(H.make_batch(oracle_layers[0], 0, B))
+    cpu = H.oracle_loop(oracle_layers, B, epochs, freq)
+    cpu.set_input(batch); cpu.init_optimize(); cpu.optimize()
+    ref = cpu.get_pred_result()
+    sdf = sdf_loss.SDFLoss(cuda_layers[0].faces, cuda_layers[1].faces).cuda()
+    gpu = HL.HostLoopOracle(cuda_layers[0], cuda_layers[0].faces, cuda_layers[1].faces, sdf, B,
+                            strategy=HL.opt_default_strategy(epochs), save_mid_freq=freq, device="cuda")
+    gpu.set_input(batch); gpu.init_optimize(); gpu.optimize()
+    res = gpu.get_pred_result()
+    assert np.abs(res["pred_joints_3d"] - ref["pred_joints_3d"]).max() <= JOINT_TOL
+    assert np.abs(res["pred_left_hand_verts"] - ref["pred_left_hand_verts"]).max() <= JOINT_TOL
+    assert np.abs(res["collision_loss_origin_scale"] - ref["collision_loss_origin_scale"]).max() <= JOINT_TOL
+
+
+def test_determinism_and_shard_invariance(model_root, oracle_layers):
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default, with_epochs
+    B = 8
+    data = H.make_batch(oracle_layers[0], 0, B)
+    strat = with_epochs(opt_default, 3)
+
+    def run(rows, bs_norm):
+        sub = {k: v[rows] for k, v in data.items()}
+        m = OptimizeModel(H.make_opt(model_root, len(rows), save_mid_freq=1, strategy=strat, bs_norm=bs_norm))
+        m.set_input(H.torch_batch(sub)); m.init_optimize(); m.optimize(0, 1)
+        return m.get_pred_result()
+
+    full1, full2 = run(list(range(B)), B), run(list(range(B)), B)
+    halves = [run(list(range(0, 4)), B), run(list(range(4, 8)), B)]
+    for k in ("pred_pose_params", "pred_shape_params", "pred_hand_trans", "pred_joints_3d", "collision_loss"):
+        assert np.array_equal(full1[k], full2[k]), k                       # run-to-run bitwise
+        assert np.array_equal(np.concatenate([h[k] for h in halves]), full1[k]), k   # sharding bitwise
