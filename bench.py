@@ -1,0 +1,339 @@
+"""Benchmark of the IHMR-OPT refinement hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one full refinement of one batch: the four opt_default stages with epoch=24
+(4 x 25 = 100 fwd+bwd+Adam iterations, snapshots every 10, online selection) plus the final
+forward, on `--frames` synthetic two-hand frames per GPU (default 65536: config 4 of
+BASELINE.json; frames are independent so ranks hold disjoint blocks, scaling = weak), followed
+by the one all-gather of refined parameters + loss statistics when N > 1.
+
+Prints ONE JSON line (rank 0).  `value` = frames refined per second with the batch resident in
+HBM; `e2e` = the same through the public OptimizeModel API from pinned host buffers (H2D of the
+17 input tensors and D2H of the 13 result arrays inside the timed region); `roofline` = the
+dominant kernel's algorithmic bytes / measured device time against MEASURED_PEAKS.json;
+`cpu_baseline` = the oracle port of the reference loop timed on this box's host cores.
+`--impl reference` times that CPU loop alone with the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "two-hand frames refined/sec (fixed iters)"
+EPOCHS, FREQ, BS_NORM = 24, 10, 512           # 4 x 25 iterations, bs_norm 512
+ITERS = 4 * (EPOCHS + 1)
+
+# Algorithmic bytes per launch unit: compulsory op-boundary traffic, fp32.
+ALG_BYTES = {                       # per hand unless noted
+    "pose_prep": 58 * 4 + 152 * 4 + 192 * 4 + 48 * 4,
+    "blend_fwd": 152 * 4 + 2334 * 4,
+    "skin_fwd": 2334 * 4 + 192 * 4 + 2334 * 4,
+    "sdf": 43572 / 2,               # 43,572 B per FRAME
+    "frame_loss": (48 * 4 + 15 * 4 + 63 * 4 + 122 * 4) / 1,
+    "skin_bwd": 2334 * 4 * 3 + 192 * 4 * 2,
+    "blend_bwd": 2334 * 4 + 152 * 4,
+    "pose_bwd": 192 * 4 + 48 * 4 + 152 * 4 + 58 * 4,
+    "step": 61 * 4 * 5,
+}
+STEP_BYTES_PER_FRAME_ITER = 76388   # SURVEY §8(d) op-boundary figure for the fused step
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def cpu_loop_sample(model_root, epochs, threads=None):
+    """Oracle port of the reference host loop + oracle leaves on the host cores: one frame,
+    `epochs` per stage. Returns (seconds, iterations, threads)."""
+    from oracle import mano_oracle
+    from tests import helpers as H
+    if threads:
+        torch.set_num_threads(threads)
+    right = mano_oracle.create(os.path.join(model_root, "MANO_RIGHT.pkl"), "mano", use_pca=False, is_rhand=True)
+    left = mano_oracle.create(os.path.join(model_root, "MANO_LEFT.pkl"), "mano", use_pca=False, is_rhand=False)
+    batch = H.torch_batch(H.make_batch(right, 0, 1))
+    loop = H.oracle_loop((right, left), 1, epochs, FREQ, bs_norm=BS_NORM)
+    t0 = time.perf_counter()
+    loop.set_input(batch)
+    loop.init_optimize()
+    loop.optimize()
+    loop.get_pred_result()
+    return time.perf_counter() - t0, 4 * (epochs + 1), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ihmr_b200 import synthetic
+    root = tempfile.mkdtemp(prefix="ihmr_ref_")
+    synthetic.write_mano_pkls(root, seed=0)
+    ep = 1                                     # bounded sample: 1 frame x 4 stages x 2 iterations (+ final forward)
+    for _ in range(args.warmup):
+        cpu_loop_sample(root, 0)
+    times = []
+    for _ in range(args.steps):
+        sec, iters, thr = cpu_loop_sample(root, ep)
+        times.append(sec)
+    sec = float(np.mean(times))
+    # scale the sample (iters fwd+bwd + 1 final fwd ~ iters + 0.5) to the 100-iteration workload
+    full = sec * (ITERS + 0.5) / (iters + 0.5)
+    value = 1.0 / full
+    sample = f"1 frame x {iters} iterations (+final forward) per step, scaled to {ITERS} iterations"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": thr, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"IHMR-OPT full loop (BASELINE config 4): {args.frames} synthetic two-hand frames per GPU x "
+                        f"{ITERS} iterations (opt_default, epoch={EPOCHS}/stage, save_mid_freq={FREQ}, bs_norm={BS_NORM})",
+            "frames_per_gpu": args.frames, "global_frames": args.frames * world, "iterations": ITERS,
+            "frame_mode": args.mode, "parallelism": f"frame-sharded x{world}, one all-gather at the end",
+            "l2": "per-step working set (~82 KB/frame of intermediates) is far larger than the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=65536, help="frames per GPU")
+    ap.add_argument("--mode", default="typical", choices=["typical", "collision"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch.distributed as dist
+    from ihmr_b200 import _lib, synthetic
+    from ihmr_b200 import dist as idist
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default, with_epochs
+    from tests import helpers as H
+
+    rank, world, local_rank = idist.init_from_env("nccl")
+    assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    F = args.frames
+    root = tempfile.mkdtemp(prefix=f"ihmr_bench_{rank}_")
+    synthetic.write_mano_pkls(root, seed=0)
+    strategy = with_epochs(opt_default, EPOCHS)
+    opt = H.make_opt(root, F, save_mid_freq=FREQ, strategy=strategy, bs_norm=BS_NORM)
+    model = OptimizeModel(opt, device=dev)
+
+    # synthetic frames of this rank (ids rank*F ...), targets from the CUDA MANO layer (untimed)
+    raw = synthetic.make_raw_frames(rank * F, F, seed=0, mode=args.mode)
+
+    def fwd(pose, shape, trans):
+        B = pose.shape[0]
+        out = np.empty((B, 42, 3), np.float32)
+        layer = model.mano_models["right"].to(dev)
+        M = torch.tensor([1.0, -1.0, -1.0], device=dev)
+        X = torch.tensor([-1.0, 1.0, 1.0], device=dev)
+        for s in range(0, B, 8192):
+            p = torch.tensor(pose[s:s + 8192], device=dev)
+            sh = torch.tensor(shape[s:s + 8192], device=dev)
+            t = torch.tensor(trans[s:s + 8192], device=dev)
+            b = p.shape[0]
+            with torch.no_grad():
+                o = layer(global_orient=torch.cat([p[:, 0:3], p[:, 48:51] * M]).contiguous(),
+                          hand_pose=torch.cat([p[:, 3:48], (p[:, 51:96].reshape(b, 15, 3) * M).reshape(b, 45)]).contiguous(),
+                          betas=torch.cat([sh[:, :10], sh[:, 10:]]).contiguous())
+                j = torch.cat([o.joints, o.vertices[:, [744, 320, 443, 554, 671]]], 1)
+                rj, lj = j[:b], j[b:] * X
+                lj = lj + (t.view(b, 1, 3) + rj[:, 0:1] - lj[:, 0:1])
+                out[s:s + b] = torch.cat([rj, lj], 1).cpu().numpy()
+        return out
+
+    data = synthetic.finish_frames(raw, fwd)
+    batch = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in data.items()}
+    h2d = sum(v.numel() * v.element_size() for k, v in batch.items() if k not in ("scale_ratio", "index"))
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def gather():
+        local = idist.pack_results(model.params, model.collision_loss_batch, model.joints_3d_loss_p_batch)
+        return idist.all_gather_results(local, F * world)
+
+    def step_resident():
+        model.init_optimize()
+        model.optimize(0, 1)
+        return gather()
+
+    def step_e2e():
+        model.set_input(batch)
+        model.init_optimize()
+        model.optimize(0, 1)
+        res = model.get_pred_result()
+        gather()
+        return res
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    model.set_input(batch)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.load().ihmr_launch_count()
+    ms_total, _ = timed(step_resident, args.steps)
+    launches = _lib.load().ihmr_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * F / (ms_step * 1e-3)
+
+    step_e2e()                                    # warm the pinned staging buffers
+    ms_e2e, res = timed(step_e2e, max(1, min(args.steps, 2)))
+    ms_e2e /= max(1, min(args.steps, 2))
+    d2h = sum(v.nbytes for k, v in res.items() if k not in ("do_flip", "pred_hand_type"))
+
+    # per-kernel device time of one iteration of every stage (separate pass, CUDA events per launch)
+    model.init_optimize()
+    per_stage = []
+    for stage in strategy:
+        model.profile_iteration(stage)
+        acc = None
+        reps = 3
+        for _ in range(reps):
+            ms = model.profile_iteration(stage)
+            acc = ms if acc is None else {k: acc[k] + ms[k] for k in ms}
+        per_stage.append({k: v / reps for k, v in acc.items()})
+    mean_ms = {k: float(np.mean([s[k] for s in per_stage])) for k in per_stage[0]}
+    dom = max(mean_ms, key=mean_ms.get)
+    units = F if dom in ("frame_loss", "step") else 2 * F
+    peak, peak_kind = load_peaks()
+    achieved = ALG_BYTES[dom] * units / (mean_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if dom in t.get("kernels", {}):
+            traffic = t["kernels"][dom]["dram_bytes_per_unit"] * units
+    iter_ms = sum(mean_ms.values())
+    step_achieved = STEP_BYTES_PER_FRAME_ITER * F / (iter_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "us_per_frame_iteration": ms_step * 1e3 / (F * ITERS),
+            "e2e": {"value": world * F / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_kind} copy bandwidth",
+                         "avg_launch_ms": mean_ms[dom], "alg_bytes_per_launch": ALG_BYTES[dom] * units},
+            "step_roofline": {"bound": "hbm", "alg_bytes_per_frame_iteration": STEP_BYTES_PER_FRAME_ITER,
+                              "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+                              "iteration_ms": iter_ms, "kernel_ms": mean_ms,
+                              "kernel_ms_per_stage": per_stage},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sec, iters, thr = cpu_loop_sample(root, 5)
+            full = sec * (ITERS + 0.5) / (iters + 0.5)
+            line["cpu_baseline"] = {"value": 1.0 / full, "unit": "frames/s", "cores": thr, "kind": "port",
+                                    "sample": f"1 frame x {iters} iterations (+final forward) = {sec:.1f} s on "
+                                              f"{thr} threads of {os.cpu_count()} CPUs, scaled to {ITERS} iterations",
+                                    "host_cpus": os.cpu_count()}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

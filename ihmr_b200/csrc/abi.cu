@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "kernels.cuh"
@@ -9,6 +10,9 @@
 namespace ihmr {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -25,6 +29,8 @@ int opt_value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* par
 int opt_final(const ihmr_model* m, int B, const float* params, const ihmr_targets_t* tg, float* right_verts,
               float* left_verts, float* joints_3d, float* collision_loss, float* collision_origin,
               float* j3d_loss_p, void* ws, cudaStream_t st);
+int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr_targets_t* tg,
+                          const ihmr_stage_t* stg, float* ms, void* ws, cudaStream_t st);
 
 template <typename T>
 static int upload(T** dst, const std::vector<T>& host) {
@@ -81,6 +87,7 @@ extern "C" {
 
 const char* ihmr_last_error(void) { return g_err; }
 int ihmr_abi_version(void) { return 1; }
+unsigned long long ihmr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int ihmr_model_create(const float* v_template, const float* shapedirs, const float* posedirs,
                       const float* J_regressor, const float* lbs_weights, const int32_t* parents,
@@ -265,6 +272,17 @@ int ihmr_opt_value_and_grad(const ihmr_model_t* m, int B, int bs_norm, const flo
     if (workspace_bytes < opt_ws_bytes(B)) { set_error("workspace too small: %zu < %zu", workspace_bytes, opt_ws_bytes(B)); return IHMR_E_WORKSPACE; }
     DeviceGuard guard(m->device);
     return opt_value_and_grad(m, B, bs_norm, params, targets, stage, losses6, grad, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_opt_profile_iteration(const ihmr_model_t* m, int B, int bs_norm, float* params,
+                               const ihmr_targets_t* targets, const ihmr_stage_t* stage, float* ms_per_kernel,
+                               void* workspace, size_t workspace_bytes, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && B > 0 && bs_norm > 0 && params && workspace && ms_per_kernel);
+    int rc;
+    if ((rc = check_targets(targets)) || (rc = check_stage(stage))) return rc;
+    if (workspace_bytes < opt_ws_bytes(B)) { set_error("workspace too small: %zu < %zu", workspace_bytes, opt_ws_bytes(B)); return IHMR_E_WORKSPACE; }
+    DeviceGuard guard(m->device);
+    return opt_profile_iteration(m, B, bs_norm, params, targets, stage, ms_per_kernel, workspace, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

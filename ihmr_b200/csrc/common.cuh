@@ -23,6 +23,7 @@ constexpr int P_CAM = 0, P_TRANS = 3, P_POSE = 6, P_SHAPE = 102;
 constexpr int P_R_ORIENT = 6, P_R_POSE = 9, P_L_ORIENT = 54, P_L_POSE = 57, P_R_SHAPE = 102, P_L_SHAPE = 112;
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of this library passes through IHMR_LAUNCH_OK
 
 #define IHMR_CUDA_OK(expr)                                                              \
     do {                                                                                \
@@ -42,6 +43,7 @@ void set_error(const char* fmt, ...);
                             __FILE__, __LINE__);                                        \
             return IHMR_E_CUDA;                                                         \
         }                                                                               \
+        ihmr::count_launch();                                                           \
     } while (0)
 
 }  // namespace ihmr

@@ -402,14 +402,29 @@ static size_t opt_ws_layout(void* base, int B, OptWs* out) {
 
 size_t opt_ws_bytes(int B) { return opt_ws_layout(nullptr, B, nullptr); }
 
+// Optional per-kernel timing of one iteration (ihmr_opt_profile_iteration): an event is
+// recorded on the stream after each kernel class.  Off on the normal path.
+constexpr int N_KERNEL_CLASSES = 9;   // pose_prep blend_fwd skin_fwd sdf frame_loss skin_bwd blend_bwd pose_bwd step
+struct IterProf {
+    cudaEvent_t ev[N_KERNEL_CLASSES + 1];
+    cudaStream_t st;
+    void tick(int i) { cudaEventRecord(ev[i], st); }
+};
+#define IHMR_TICK(prof, i) do { if (prof) (prof)->tick(i); } while (0)
+
 // forward of both hands of every frame: X, A, joints, off, verts
-static int forward_all(const ihmr_model* m, int B, const float* params, OptWs& w, cudaStream_t st) {
+static int forward_all(const ihmr_model* m, int B, const float* params, OptWs& w, cudaStream_t st,
+                       IterProf* prof = nullptr) {
     HandSrc src;
     src.params = params;
     int rc;
+    IHMR_TICK(prof, 0);
     if ((rc = launch_pose_prep(m, 2 * B, src, w.mano.X, w.mano.A, w.joints, st))) return rc;
+    IHMR_TICK(prof, 1);
     if ((rc = launch_blend_fwd(m, 2 * B, w.mano.X, w.mano.off, st))) return rc;
+    IHMR_TICK(prof, 2);
     if ((rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st))) return rc;
+    IHMR_TICK(prof, 3);
     return IHMR_OK;
 }
 
@@ -430,26 +445,32 @@ static FrameLossArgs base_loss_args(int B, int bs_norm, const float* params, con
 
 // value + gradient of one iteration into w.grad (and optionally the six batch losses)
 static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* params, const ihmr_targets_t* tg,
-                          const ihmr_stage_t* stg, OptWs& w, FrameLossArgs& la, cudaStream_t st) {
+                          const ihmr_stage_t* stg, OptWs& w, FrameLossArgs& la, cudaStream_t st,
+                          IterProf* prof = nullptr) {
     int rc;
-    if ((rc = forward_all(m, B, params, w, st))) return rc;
+    if ((rc = forward_all(m, B, params, w, st, prof))) return rc;
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
     sa.losses = w.col_loss; sa.gverts = w.gverts; sa.gshift = w.gshift;
     sa.grad_scale = stg->w_collision / (float)bs_norm;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
+    IHMR_TICK(prof, 4);
     la.gshift_col = w.gshift;
     la.gjoints16 = w.gjoints; la.gtips = w.gtips; la.grad = w.grad;
     la.j2d_batch = w.j2d_b; la.j3d_batch = w.j3d_b;
     k_frame_loss<<<B, FL_THREADS, 0, st>>>(la);
     IHMR_LAUNCH_OK();
+    IHMR_TICK(prof, 5);
     if ((rc = launch_skin_bwd(m, 2 * B, w.mano.off, w.mano.A, w.gverts, w.gtips, w.mano.gposed, w.mano.dA, st))) return rc;
+    IHMR_TICK(prof, 6);
     if ((rc = launch_blend_bwd(m, 2 * B, w.mano.gposed, w.mano.dX, st))) return rc;
+    IHMR_TICK(prof, 7);
     HandSrc src;
     src.params = params;
     HandGrad hg;
     hg.params_grad = w.grad;
     if ((rc = launch_pose_bwd(m, 2 * B, src, w.mano.dA, w.gjoints, w.mano.dX, hg, st))) return rc;
+    IHMR_TICK(prof, 8);
     return IHMR_OK;
 }
 
@@ -491,6 +512,32 @@ int opt_stage(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr
     }
     k_restore<<<nblk, nthr, 0, st>>>(B, stg->update_mask, params, w.best_params);
     IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+// One iteration (forward, losses, backward, optimiser step on a scratch copy of nothing: the
+// parameters ARE updated) with an event after every kernel class; synchronises the stream.
+int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr_targets_t* tg,
+                          const ihmr_stage_t* stg, float* ms, void* ws, cudaStream_t st) {
+    OptWs w;
+    opt_ws_layout(ws, B, &w);
+    IterProf prof;
+    prof.st = st;
+    for (auto& e : prof.ev) IHMR_CUDA_OK(cudaEventCreate(&e));
+    FrameLossArgs la = base_loss_args(B, bs_norm, params, tg, stg, w);
+    int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, &prof);
+    if (rc) return rc;
+    StepArgs sa{};
+    sa.B = B; sa.mask = stg->update_mask; sa.optimizer = IHMR_OPT_ADAM; sa.lr = 0.f;   // lr 0: parameters unchanged
+    sa.step_size = 0.f; sa.bc2_sqrt = 1.f; sa.eps = 1e-8f; sa.momentum = 0.9f; sa.first_step = 1;
+    sa.params = params; sa.grad = w.grad; sa.m = w.m; sa.v = w.v; sa.take = nullptr; sa.best_params = w.best_params;
+    const int nthr = 256, nblk = (int)(((size_t)B * PD + nthr - 1) / nthr);
+    k_step<<<nblk, nthr, 0, st>>>(sa);
+    IHMR_LAUNCH_OK();
+    prof.tick(9);
+    IHMR_CUDA_OK(cudaStreamSynchronize(st));
+    for (int i = 0; i < N_KERNEL_CLASSES; ++i) IHMR_CUDA_OK(cudaEventElapsedTime(&ms[i], prof.ev[i], prof.ev[i + 1]));
+    for (auto& e : prof.ev) cudaEventDestroy(e);
     return IHMR_OK;
 }
 

@@ -71,6 +71,7 @@ class OptimizeModel:
         assert abs(self.default_loss_weights["collision_loss_weight"] - 1.0) < 1e-7
         self._ws = None
         self._buf: Dict[str, torch.Tensor] = {}
+        self._pinned: Dict[str, torch.Tensor] = {}
 
     def _build_device_model(self):
         from .mano_layer import DeviceModel
@@ -189,18 +190,43 @@ class OptimizeModel:
         return losses, grad
 
     # ------------------------------------------------------------------------- output
+    def _to_host(self, name: str, t: torch.Tensor) -> np.ndarray:
+        """D2H through a cached pinned staging buffer (async on the current stream)."""
+        t = t.detach().contiguous()
+        buf = self._pinned.get(name)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned[name] = buf
+        buf.copy_(t, non_blocking=True)
+        return buf.numpy()
+
     def get_pred_result(self):
-        """optimize_model.py:418-435: the 13 numpy arrays the evaluator consumes."""
-        c = lambda t: t.detach().cpu().numpy()
+        """optimize_model.py:418-435: the 13 numpy arrays the evaluator consumes. The arrays
+        are views of pinned staging buffers and stay valid until the next call."""
         B = self.batch_size
-        return OrderedDict(
-            pred_cam_params=c(self.pred_cam_params), pred_hand_trans=c(self.pred_hand_trans),
-            pred_shape_params=c(self.pred_shape_params), pred_pose_params=c(self.pred_pose_params),
-            pred_right_hand_verts=c(self.pred_right_hand_verts), pred_left_hand_verts=c(self.pred_left_hand_verts),
-            mano_params_weight=c(self.mano_params_weight), pred_joints_3d=c(self.pred_joints_3d),
-            gt_joints_3d=c(self.joints_3d), collision_loss=c(self.collision_loss_batch),
-            collision_loss_origin_scale=c(self.collision_loss_origin_scale),
+        c = self._to_host
+        res = OrderedDict(
+            pred_cam_params=c("cam", self.pred_cam_params), pred_hand_trans=c("trans", self.pred_hand_trans),
+            pred_shape_params=c("shape", self.pred_shape_params), pred_pose_params=c("pose", self.pred_pose_params),
+            pred_right_hand_verts=c("rv", self.pred_right_hand_verts),
+            pred_left_hand_verts=c("lv", self.pred_left_hand_verts),
+            mano_params_weight=c("mpw", self.mano_params_weight), pred_joints_3d=c("j3d", self.pred_joints_3d),
+            gt_joints_3d=c("gtj3d", self.joints_3d), collision_loss=c("col", self.collision_loss_batch),
+            collision_loss_origin_scale=c("ori", self.collision_loss_origin_scale),
             do_flip=np.zeros(B).astype(np.int32), pred_hand_type=np.ones(B).astype(np.int32))
+        torch.cuda.current_stream(self.device).synchronize()     # the one sync of the batch
+        return res
+
+    def profile_iteration(self, stage: dict):
+        """Device milliseconds of each kernel class for one iteration of `stage` (measurement aid)."""
+        ws = self._workspace()
+        st = _lib.make_stage(stage)
+        ms = (C.c_float * len(_lib.KERNEL_CLASSES))()
+        _lib.check(self.lib.ihmr_opt_profile_iteration(self._model.handle, self.batch_size, self.bs_norm,
+                                                       _ptr(self.params), C.byref(self._targets), C.byref(st), ms,
+                                                       _ptr(ws), ws.numel(), _stream(self.device)),
+                   "ihmr_opt_profile_iteration")
+        return dict(zip(_lib.KERNEL_CLASSES, [float(x) for x in ms]))
 
     def get_current_errors(self):
         """optimize_model.py:438-455 (log-only values; plain tensor arithmetic on the exported

@@ -46,6 +46,8 @@ typedef void* ihmr_stream_t; /* cudaStream_t */
 
 const char* ihmr_last_error(void);
 int ihmr_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long ihmr_launch_count(void);
 
 /* ---- model constants ------------------------------------------------------------------
  * Replaces `smplx.create(path, 'mano', use_pca=False, is_rhand=..., batch_size=...)` plus
@@ -144,6 +146,15 @@ int ihmr_opt_value_and_grad(const ihmr_model_t* model, int n_frames, int bs_norm
                             const ihmr_targets_t* targets, const ihmr_stage_t* stage, float* losses6,
                             float* grad, void* workspace, size_t workspace_bytes,
                             ihmr_stream_t stream);
+
+/* Measurement aid (the one entry point that synchronises `stream`): runs ONE iteration of the
+ * stage (forward, losses, backward, a zero-length optimiser step) with a CUDA event after each
+ * kernel class and returns the 9 device times in milliseconds:
+ * [pose_prep, blend_fwd, skin_fwd, sdf, frame_loss, skin_bwd, blend_bwd, pose_bwd, step]. */
+int ihmr_opt_profile_iteration(const ihmr_model_t* model, int n_frames, int bs_norm, float* params,
+                               const ihmr_targets_t* targets, const ihmr_stage_t* stage,
+                               float* ms_per_kernel, void* workspace, size_t workspace_bytes,
+                               ihmr_stream_t stream);
 
 #ifdef __cplusplus
 }
