@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <vector>
 
@@ -51,6 +52,48 @@ static void build_shape_rows(const float* shapedirs, const float* Jreg, std::vec
                 for (int v = 0; v < NV; ++v) acc += (double)Jreg[j * NV + v] * shapedirs[((size_t)v * 3 + c) * NB + k];
                 Js[k * 48 + j * 3 + c] = (float)acc;
             }
+}
+
+// Static spatial clustering of the faces (rest pose): recursive median split along the longest
+// axis of the centroids into ceil(NF/32) groups of <= 32 faces.  The posed mesh is articulated,
+// so rest-pose neighbours stay neighbours and the per-frame cluster boxes stay tight.
+static void split_faces(std::vector<int>& ids, int lo, int hi, int groups, const std::vector<float>& cen,
+                        std::vector<std::vector<int>>& out) {
+    if (groups <= 1) {
+        out.emplace_back(ids.begin() + lo, ids.begin() + hi);
+        return;
+    }
+    float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = lo; i < hi; ++i)
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], cen[ids[i] * 3 + a]); mx[a] = std::max(mx[a], cen[ids[i] * 3 + a]); }
+    int ax = 0;
+    for (int a = 1; a < 3; ++a) if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
+    const int gl = groups / 2;
+    const int mid = lo + (int)((long long)(hi - lo) * gl / groups);
+    std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi,
+                     [&](int p, int q) { return cen[p * 3 + ax] < cen[q * 3 + ax] || (cen[p * 3 + ax] == cen[q * 3 + ax] && p < q); });
+    split_faces(ids, lo, mid, gl, cen, out);
+    split_faces(ids, mid, hi, groups - gl, cen, out);
+}
+
+static std::vector<uint16_t> cluster_table(const float* v_template, const int32_t* faces) {
+    constexpr int ncl = (NF + 31) / 32;
+    std::vector<float> cen(NF * 3);
+    for (int f = 0; f < NF; ++f)
+        for (int a = 0; a < 3; ++a)
+            cen[f * 3 + a] = (v_template[faces[f * 3] * 3 + a] + v_template[faces[f * 3 + 1] * 3 + a] + v_template[faces[f * 3 + 2] * 3 + a]) / 3.f;
+    std::vector<int> ids(NF);
+    for (int f = 0; f < NF; ++f) ids[f] = f;
+    std::vector<std::vector<int>> groups;
+    split_faces(ids, 0, NF, ncl, cen, groups);
+    std::vector<uint16_t> tab((size_t)ncl * 32 * 4, 0);
+    for (int c = 0; c < ncl; ++c)
+        for (size_t i = 0; i < groups[c].size() && i < 32; ++i) {
+            const int f = groups[c][i];
+            uint16_t* t = &tab[((size_t)c * 32 + i) * 4];
+            t[0] = (uint16_t)faces[f * 3]; t[1] = (uint16_t)faces[f * 3 + 1]; t[2] = (uint16_t)faces[f * 3 + 2]; t[3] = 1;
+        }
+    return tab;
 }
 
 static std::vector<float> transpose_D(const std::vector<float>& D) {
@@ -140,7 +183,9 @@ int ihmr_model_create(const float* v_template, const float* shapedirs, const flo
     if ((rc = upload(&m->D, D)) || (rc = upload(&m->DT, DT)) || (rc = upload(&m->vtemp, vt)) ||
         (rc = upload(&m->Jt, Jt)) || (rc = upload(&m->Js, Js)) || (rc = upload(&m->Wt, Wt)) ||
         (rc = upload(&m->W4, W4)) || (rc = upload(&m->hands_mean, hm)) || (rc = upload(&m->Jreg, Jreg)) ||
-        (rc = upload(&m->faces[0], fr)) || (rc = upload(&m->faces[1], fl))) {
+        (rc = upload(&m->faces[0], fr)) || (rc = upload(&m->faces[1], fl)) ||
+        (rc = upload(&m->cl_tri[0], cluster_table(v_template, faces_right))) ||
+        (rc = upload(&m->cl_tri[1], cluster_table(v_template, faces_left)))) {
         ihmr_model_destroy(m);
         return rc;
     }
@@ -153,7 +198,7 @@ void ihmr_model_destroy(ihmr_model_t* m) {
     DeviceGuard guard(m->device);
     cudaFree(m->D); cudaFree(m->DT); cudaFree(m->vtemp); cudaFree(m->Jt); cudaFree(m->Js);
     cudaFree(m->Wt); cudaFree(m->W4); cudaFree(m->hands_mean); cudaFree(m->Jreg);
-    cudaFree(m->faces[0]); cudaFree(m->faces[1]);
+    cudaFree(m->faces[0]); cudaFree(m->faces[1]); cudaFree(m->cl_tri[0]); cudaFree(m->cl_tri[1]);
     delete m;
 }
 
@@ -221,6 +266,15 @@ int ihmr_sdf_loss(const ihmr_model_t* m, int n_frames, const float* hand_verts, 
     SdfArgs a;
     a.verts = hand_verts; a.losses = losses; a.per_vert = per_vert; a.origin = origin_scale;
     a.gverts = grad_hand_verts; a.robustifier = robustifier;
+    return launch_sdf(m, n_frames, a, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_sdf_stats(const ihmr_model_t* m, int n_frames, const float* hand_verts, float* losses, int* stats,
+                   ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && n_frames >= 0 && hand_verts && losses && stats);
+    DeviceGuard guard(m->device);
+    SdfArgs a;
+    a.verts = hand_verts; a.losses = losses; a.stats = stats;
     return launch_sdf(m, n_frames, a, static_cast<cudaStream_t>(stream));
 }
 

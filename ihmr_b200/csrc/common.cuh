@@ -62,5 +62,6 @@ struct ihmr_model {
     float* hands_mean;  // (48) [0,0,0, hands_mean(45)]
     float* Jreg;     // (16, 778)  kept for update_shapedirs
     uint16_t* faces[2];  // (1538, 4) u16 per hand (right, left), 4th lane unused
+    uint16_t* cl_tri[2]; // (49 clusters x 32, 4) u16: vertex ids of the faces of each spatial cluster, lane 3 = valid
     int parents[16];
 };

@@ -340,8 +340,8 @@ __global__ void k_loss_reduce(int B, const float* parts, float wcol, float* out)
 // final export: world-frame vertices of both hands (optimize_model.py:204-228)
 __global__ void k_export_verts(int B, const float* verts, const float* joints16, const float* params,
                                float* right, float* left) {
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
     if (i >= NV) return;
     const float* jr = joints16 + ((size_t)b * 2 + 0) * 48;
     const float* jl = joints16 + ((size_t)b * 2 + 1) * 48;
@@ -579,7 +579,7 @@ int opt_final(const ihmr_model* m, int B, const float* params, const ihmr_target
     k_frame_loss<<<B, FL_THREADS, 0, st>>>(la);
     IHMR_LAUNCH_OK();
     if (right_verts && left_verts) {
-        dim3 grid((NV + 255) / 256, B);
+        dim3 grid(B, (NV + 255) / 256);
         k_export_verts<<<grid, 256, 0, st>>>(B, w.verts, w.joints, params, right_verts, left_verts);
         IHMR_LAUNCH_OK();
     }

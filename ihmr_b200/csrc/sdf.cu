@@ -25,6 +25,8 @@ constexpr int SDF_THREADS = 256;
 constexpr int SDF_SLOTS = 4;        // 4 x 256 >= 778 query vertices
 constexpr int PHI_CAP = 4096;       // voxels evaluated per pass
 constexpr int BIN_CAP = 6144;       // (face, lattice cell) pairs
+constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
+constexpr int SDF_MAX_RING = 2;     // lattice rings searched per voxel before the cluster search takes over
 
 struct __align__(16) SdfSmem {
     float U[NV * 3];
@@ -34,12 +36,17 @@ struct __align__(16) SdfSmem {
     uint16_t bin_start[G * G + 2];
     uint16_t bin_entries[BIN_CAP];
     uint16_t worklist[PHI_CAP];
+    uint16_t far_list[PHI_CAP]; // voxels whose nearest face is beyond the ring search
     float phi[PHI_CAP];
+    float cl_box[NCL * 6];      // bounding boxes of the static face clusters (lo xyz, hi xyz)
+    uint32_t col_mask[G];       // lattice columns that hold a marked & inside voxel
+    uint32_t near_mask[G];      // ... dilated by SDF_MAX_RING columns
     float red[64];
     float box[2][2][3];         // [hand][lo/hi][xyz]
     float shift[4];
     int scan_warp[8];
-    int scalars[4];
+    int far_count;
+    int scalars[3];
 };
 
 __device__ __forceinline__ float voxel_center(int i) { return (2.0f * i + 1.0f - G) / G; }
@@ -163,44 +170,134 @@ __device__ __forceinline__ int lattice_cell(float y) {   // cell of width 2/G ce
     return min(G - 1, max(0, c));
 }
 
-// phi of one voxel: min distance to the mesh, ring search over the lattice bins
-__device__ float eval_voxel(const SdfSmem& s, const uint16_t* __restrict__ faces, int code, bool use_bins) {
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ((SDF_MAX_RING + 0.5) cells)^2: a voxel whose nearest face is farther cannot be finished by the ring search
+constexpr float SDF_NEAR_LIMIT2 = ((SDF_MAX_RING + 0.5f) * (2.0f / G)) * ((SDF_MAX_RING + 0.5f) * (2.0f / G));
+
+// lower bound of the squared distance from a voxel to the mesh: nearest cluster bounding box
+// (the 8 lanes of an octet split the clusters; all 32 lanes must call this)
+__device__ __forceinline__ float cluster_lower_bound_octet(const SdfSmem& s, int code, int gl) {
     const int x = code & 31, col = code >> 5, j = col & 31, k = col >> 5;
     const float q[3] = {voxel_center(x), voxel_center(j), voxel_center(k)};
-    float best = 1e30f;
-    if (use_bins) {
-        const float h = 2.0f / G;
-        for (int ring = 0; ring < G; ++ring) {
-            if (ring > 0) {
-                const float lb = (ring - 0.5f) * h - 1e-5f;
-                if (lb * lb >= best) break;
-            }
-            for (int kk = k - ring; kk <= k + ring; ++kk) {
-                if (kk < 0 || kk >= G) continue;
-                const bool edge_row = (kk == k - ring) || (kk == k + ring);
-                const int step = edge_row ? 1 : max(1, 2 * ring);
-                for (int jj = j - ring; jj <= j + ring; jj += step) {
-                    if (jj < 0 || jj >= G) continue;
-                    const int c = kk * G + jj;
-                    for (int e = s.bin_start[c]; e < s.bin_start[c + 1]; ++e) {
-                        const int f = s.bin_entries[e];
-                        const ushort4 id = reinterpret_cast<const ushort4*>(faces)[f];
-                        best = fminf(best, pt_tri_dist2(q, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z));
-                    }
-                }
-            }
+    float lb = 1e30f;
+    for (int c = gl; c < NCL; c += 8) {
+        const float* bx = s.cl_box + c * 6;
+        float d2 = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float d = fmaxf(fmaxf(bx[a] - q[a], q[a] - bx[3 + a]), 0.f);
+            d2 += d * d;
         }
-    } else {
-        for (int f = 0; f < NF; ++f) {
-            const ushort4 id = reinterpret_cast<const ushort4*>(faces)[f];
+        lb = fminf(lb, d2);
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) lb = fminf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+    return lb;
+}
+
+// Squared distance from voxel `code` to the nearest face found in the lattice bins within
+// SDF_MAX_RING rings of its (y,z) column, computed by an OCTET (8 consecutive lanes) per voxel.
+// `done` tells whether the result is certified: a face not binned within ring r has every point
+// farther than (r + 0.5) cells away, so best <= ((SDF_MAX_RING + 0.5) cells)^2 is the exact
+// minimum over ALL faces.  Own column first (it holds the faces the voxel's x-ray crosses, a
+// good upper bound), then the 24 neighbour columns with two cheap rejections: the column's
+// (y,z) offset and the face's x-extent.  All 32 lanes must call this (shuffles).
+__device__ __forceinline__ float eval_voxel_near(const SdfSmem& s, const uint16_t* __restrict__ faces, int code,
+                                                 bool valid, int lane, bool& done) {
+    const int gl = lane & 7;
+    const int x = code & 31, col = code >> 5, j = col & 31, k = col >> 5;
+    const float q[3] = {voxel_center(x), voxel_center(j), voxel_center(k)};
+    const ushort4* f4 = reinterpret_cast<const ushort4*>(faces);
+    const float h = 2.0f / G;
+    float best = 1e30f;
+    if (valid) {
+        for (int e = s.bin_start[col] + gl; e < s.bin_start[col + 1]; e += 8) {
+            const ushort4 id = f4[s.bin_entries[e]];
             best = fminf(best, pt_tri_dist2(q, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z));
         }
     }
-    return sqrtf(best);
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (valid) {
+        constexpr int W = 2 * SDF_MAX_RING + 1;
+        for (int n = gl; n < W * W; n += 8) {
+            const int dj = n % W - SDF_MAX_RING, dk = n / W - SDF_MAX_RING;
+            if (dj == 0 && dk == 0) continue;
+            const int jj = j + dj, kk = k + dk;
+            if (jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
+            // every point of a face binned only here is at least this far away in (y,z)
+            const float oy = fmaxf(fabsf((float)dj) - 0.5f, 0.f) * h, oz = fmaxf(fabsf((float)dk) - 0.5f, 0.f) * h;
+            const float yz2 = oy * oy + oz * oz;
+            if (yz2 >= best) continue;
+            const int c = kk * G + jj;
+            for (int e = s.bin_start[c]; e < s.bin_start[c + 1]; ++e) {
+                const ushort4 id = f4[s.bin_entries[e]];
+                const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
+                const float dx = fmaxf(fmaxf(fminf(A_[0], fminf(B_[0], C_[0])) - q[0], q[0] - fmaxf(A_[0], fmaxf(B_[0], C_[0]))), 0.f);
+                if (dx * dx >= best) continue;       // x-extent alone is already too far
+                best = fminf(best, pt_tri_dist2(q, A_, B_, C_));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    done = best <= SDF_NEAR_LIMIT2 - 1e-6f;
+    return best;
+}
+
+// Exact squared distance for a far voxel, one warp per voxel: the faces are grouped at model
+// creation into NCL spatial clusters of <= 32 (cl_tri); clusters are visited nearest bounding
+// box first, one face per lane, until the nearest unvisited box is farther than the best
+// distance.  The open wrist makes some far-away voxels "inside" (odd crossing parity), and
+// the reference's brute-force loop gives them their true distance, so they must be exact too.
+__device__ __forceinline__ float eval_voxel_far(const SdfSmem& s, const ushort4* __restrict__ cl_tri, int code,
+                                                float best, int lane) {
+    const int x = code & 31, col = code >> 5, j = col & 31, k = col >> 5;
+    const float q[3] = {voxel_center(x), voxel_center(j), voxel_center(k)};
+    float lb[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int c = lane + 32 * t;
+        lb[t] = 1e30f;
+        if (c < NCL) {
+            const float* bx = s.cl_box + c * 6;
+            float d2 = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float d = fmaxf(fmaxf(bx[a] - q[a], q[a] - bx[3 + a]), 0.f);
+                d2 += d * d;
+            }
+            lb[t] = d2;
+        }
+    }
+    for (int it = 0; it < NCL; ++it) {
+        float m = fminf(lb[0], lb[1]);
+        int which = (lb[0] <= lb[1]) ? lane : lane + 32;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const int w2 = __shfl_xor_sync(0xffffffffu, which, o);
+            if (m2 < m || (m2 == m && w2 < which)) { m = m2; which = w2; }
+        }
+        if (m > best * 1.00001f) break;
+        const ushort4 id = cl_tri[which * 32 + lane];
+        float d2 = 1e30f;
+        if (id.w) d2 = pt_tri_dist2(q, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z);
+        best = fminf(best, warp_min(d2));
+        if (which == lane) lb[0] = 1e30f;
+        if (which == lane + 32) lb[1] = 1e30f;
+    }
+    return best;
 }
 
 __global__ void __launch_bounds__(SDF_THREADS)
-k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __restrict__ faces_l) {
+k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __restrict__ faces_l,
+      const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SdfSmem& s = *reinterpret_cast<SdfSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -273,6 +370,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
     for (int h = 0; h < 2; ++h) {
         const int o = 1 - h;
         const uint16_t* faces = h ? faces_l : faces_r;
+        const ushort4* cl_tri = h ? cl_l : cl_r;
         float cen[3], ext = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -328,6 +426,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             }
         }
         const bool any_block = __syncthreads_or(any);
+        if (a.stats) { const int nact = __syncthreads_count(act[0]) + __syncthreads_count(act[1]) + __syncthreads_count(act[2]) + __syncthreads_count(act[3]); if (tid == 0) a.stats[b * 8 + 4 + h] = nact; }
         bool run = any_block;
         int total = 0;
         bool use_bins = true;
@@ -347,9 +446,10 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
                 const float ymin = fminf(A_[1], fminf(B_[1], C_[1])), ymax = fmaxf(A_[1], fmaxf(B_[1], C_[1]));
                 const float zmin = fminf(A_[2], fminf(B_[2], C_[2])), zmax = fmaxf(A_[2], fmaxf(B_[2], C_[2]));
-                // lattice points y_j = (2j+1-G)/G inside [ymin,ymax], one spare on each side
-                const int j0 = max(0, (int)floorf((ymin * G + (G - 1)) * 0.5f)), j1 = min(G - 1, (int)ceilf((ymax * G + (G - 1)) * 0.5f));
-                const int k0 = max(0, (int)floorf((zmin * G + (G - 1)) * 0.5f)), k1 = min(G - 1, (int)ceilf((zmax * G + (G - 1)) * 0.5f));
+                // lattice points y_j = (2j+1-G)/G inside [ymin,ymax]
+                // (1e-3 of a cell absorbs the rounding of the index arithmetic; the ray test itself decides)
+                const int j0 = max(0, (int)ceilf((ymin * G + (G - 1)) * 0.5f - 1e-3f)), j1 = min(G - 1, (int)floorf((ymax * G + (G - 1)) * 0.5f + 1e-3f));
+                const int k0 = max(0, (int)ceilf((zmin * G + (G - 1)) * 0.5f - 1e-3f)), k1 = min(G - 1, (int)floorf((zmax * G + (G - 1)) * 0.5f + 1e-3f));
                 for (int k = k0; k <= k1; ++k)
                     for (int j = j0; j <= j1; ++j) {
                         const int col = k * G + j;
@@ -379,16 +479,31 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             run = total > 0;
         }
         if (run) {
-            // ---- bin faces by lattice cell (needed[] is free now: counters, then cursors)
-            for (int i = tid; i < G * G; i += SDF_THREADS) s.needed[i] = 0u;
+            // ---- lattice columns that can be reached by a ring search: work columns dilated by SDF_MAX_RING
+            if (tid < G) s.col_mask[tid] = 0u;
+            for (int i = tid; i < G * G; i += SDF_THREADS) s.needed[i] = 0u;   // needed[] is free now: bin counters/cursors
             __syncthreads();
+            for (int i = tid; i < G * G; i += SDF_THREADS)
+                if (s.work[i]) atomicOr(&s.col_mask[i >> 5], 1u << (i & 31));
+            __syncthreads();
+            if (tid < G) {
+                uint32_t m = 0u;
+                for (int kk = max(0, tid - SDF_MAX_RING); kk <= min(G - 1, tid + SDF_MAX_RING); ++kk) m |= s.col_mask[kk];
+                uint32_t d = m;
+#pragma unroll
+                for (int r = 1; r <= SDF_MAX_RING; ++r) d |= (m << r) | (m >> r);
+                s.near_mask[tid] = d;
+            }
+            __syncthreads();
+            // ---- bin faces by the lattice cells their bounding box overlaps (reachable cells only)
             for (int f = tid; f < NF; f += SDF_THREADS) {
                 const ushort4 id = reinterpret_cast<const ushort4*>(faces)[f];
                 const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
                 const int j0 = lattice_cell(fminf(A_[1], fminf(B_[1], C_[1]))), j1 = lattice_cell(fmaxf(A_[1], fmaxf(B_[1], C_[1])));
                 const int k0 = lattice_cell(fminf(A_[2], fminf(B_[2], C_[2]))), k1 = lattice_cell(fmaxf(A_[2], fmaxf(B_[2], C_[2])));
                 for (int k = k0; k <= k1; ++k)
-                    for (int j = j0; j <= j1; ++j) atomicAdd(&s.needed[k * G + j], 1u);
+                    for (int j = j0; j <= j1; ++j)
+                        if ((s.near_mask[k] >> j) & 1u) atomicAdd(&s.needed[k * G + j], 1u);
             }
             __syncthreads();
             int cnt[4], excl[4];
@@ -396,6 +511,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             for (int i = 0; i < 4; ++i) cnt[i] = (int)s.needed[tid * 4 + i];
             const int entries = block_scan_1024(cnt, excl, s.scan_warp);
             use_bins = entries <= BIN_CAP;
+            if (a.stats && tid == 0) a.stats[b * 8 + 6 + h] = entries;
             if (use_bins) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { s.bin_start[tid * 4 + i] = (uint16_t)excl[i]; s.needed[tid * 4 + i] = 0u; }
@@ -408,12 +524,39 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     const int k0 = lattice_cell(fminf(A_[2], fminf(B_[2], C_[2]))), k1 = lattice_cell(fmaxf(A_[2], fmaxf(B_[2], C_[2])));
                     for (int k = k0; k <= k1; ++k)
                         for (int j = j0; j <= j1; ++j) {
+                            if (!((s.near_mask[k] >> j) & 1u)) continue;
                             const int c = k * G + j;
                             const uint32_t pos = s.bin_start[c] + atomicAdd(&s.needed[c], 1u);
                             s.bin_entries[pos] = (uint16_t)f;
                         }
                 }
             }
+            // ---- bounding boxes of the static face clusters (used by the far search)
+            for (int c = tid >> 5; c < NCL; c += SDF_THREADS / 32) {
+                const ushort4 id = cl_tri[c * 32 + (tid & 31)];
+                float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+                if (id.w) {
+                    const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        lo[ax] = fminf(A_[ax], fminf(B_[ax], C_[ax]));
+                        hi[ax] = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
+                    }
+                }
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        lo[ax] = fminf(lo[ax], __shfl_xor_sync(0xffffffffu, lo[ax], o));
+                        hi[ax] = fmaxf(hi[ax], __shfl_xor_sync(0xffffffffu, hi[ax], o));
+                    }
+                }
+                if ((tid & 31) == 0) {
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) { s.cl_box[c * 6 + ax] = lo[ax]; s.cl_box[c * 6 + 3 + ax] = hi[ax]; }
+                }
+            }
+            if (tid == 0) s.far_count = 0;
             __syncthreads();
 
             // ---- passes over the marked & inside voxels
@@ -432,9 +575,31 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     }
                 }
                 __syncthreads();
-                for (int i = tid; i < pass1 - pass0; i += SDF_THREADS)
-                    s.phi[i] = eval_voxel(s, faces, s.worklist[i], use_bins);
+                // near voxels: one octet of lanes each, ring search over the bins; the rest go to far_list
+                for (int i0v = (tid >> 5) * 4; i0v < pass1 - pass0; i0v += (SDF_THREADS / 32) * 4) {
+                    const int i = i0v + ((tid & 31) >> 3);
+                    const bool valid = i < pass1 - pass0;
+                    const int code = valid ? s.worklist[i] : 0;
+                    // voxels farther than the ring search can certify go straight to the far list
+                    const float lb_cl = cluster_lower_bound_octet(s, code, tid & 7);   // shuffles: every lane calls
+                    const bool near_ok = valid && use_bins && lb_cl <= SDF_NEAR_LIMIT2;
+                    bool done = false;
+                    const float best = eval_voxel_near(s, faces, code, near_ok, tid & 31, done);
+                    if (valid && (tid & 7) == 0) {
+                        if (near_ok && done) s.phi[i] = sqrtf(best);
+                        else { s.phi[i] = best; s.far_list[atomicAdd(&s.far_count, 1)] = (uint16_t)i; }
+                    }
+                }
                 __syncthreads();
+                const int nfar = s.far_count;
+                if (a.stats && tid == 0) { a.stats[b * 8 + 2 * h] += pass1 - pass0; a.stats[b * 8 + 2 * h + 1] += nfar; }
+                for (int w = tid >> 5; w < nfar; w += SDF_THREADS / 32) {
+                    const int i = s.far_list[w];
+                    const float best = eval_voxel_far(s, cl_tri, s.worklist[i], s.phi[i], tid & 31);
+                    if ((tid & 31) == 0) s.phi[i] = sqrtf(best);
+                }
+                __syncthreads();
+                if (tid == 0) s.far_count = 0;
                 // ---- trilinear sample + gradient (grid_sampler_3d fwd/bwd, align_corners=False, zeros)
 #pragma unroll
                 for (int sl = 0; sl < SDF_SLOTS; ++sl) {
@@ -510,7 +675,9 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
         IHMR_CUDA_OK(cudaFuncSetAttribute(k_sdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SdfSmem)));
         configured = true;
     }
-    k_sdf<<<B, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, m->faces[0], m->faces[1]);
+    k_sdf<<<B, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, m->faces[0], m->faces[1],
+                                                    reinterpret_cast<const ushort4*>(m->cl_tri[0]),
+                                                    reinterpret_cast<const ushort4*>(m->cl_tri[1]));
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }

@@ -58,6 +58,10 @@ def all_gather_results(local: torch.Tensor, total_frames: int) -> torch.Tensor:
         out = torch.empty(total_frames, local.shape[1], dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local)
         return out
-    parts = [torch.empty(c, local.shape[1], dtype=local.dtype, device=local.device) for c in counts]
-    dist.all_gather(parts, local)
-    return torch.cat(parts, dim=0)
+    # uneven blocks: pad every shard to the largest, gather once, drop the padding rows
+    cmax = max(counts)
+    padded = torch.zeros(cmax, local.shape[1], dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty(world * cmax, local.shape[1], dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * cmax:r * cmax + c] for r, c in enumerate(counts)], dim=0)
