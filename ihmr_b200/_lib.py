@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libihmr_b200.so")
+LIB_PATH = os.environ.get("IHMR_B200_LIB", os.path.join(_HERE, "_lib", "libihmr_b200.so"))   # override: experiments only
 
 EXPORTS = (
     "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",

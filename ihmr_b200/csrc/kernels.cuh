@@ -64,7 +64,7 @@ struct SdfArgs {
     float* gshift = nullptr;           // (B,3) or null
     float grad_scale = 1.0f;           // gverts/gshift = grad_scale * d losses[b]/d(.)
     float robustifier = 0.0f;
-    int* stats = nullptr;              // (B,8) debug counters (zeroed by the caller), tests/tools only
+    int* stats = nullptr;              // (B,32) debug counters / phase cycles (zeroed by the caller), tests/tools only
 };
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
 

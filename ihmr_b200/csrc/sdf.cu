@@ -1,14 +1,16 @@
 // Left/right interpenetration loss, forward + backward in one kernel (SURVEY.md §8 a10,
 // Appendix B).  One CTA per frame.  For each direction (grid hand h, query hand o = 1-h):
 //
-//   1. bounding box of h -> centre c_h, scale s_h = 0.6 * max extent           (A2)
-//   2. mark the <= 8 voxel corners each query vertex touches                    (lazy grid)
+//   1. bounding box of h -> centre c_h, scale s_h = 0.6 * max extent                     (A2)
+//   2. mark the <= 8 voxel corners each query vertex touches                      (lazy grid)
 //   3. inside/outside of the marked voxel columns: every face is rasterised onto the 32x32
-//      (y,z) lattice of +x rays; a hit toggles the bits of all voxels left of the crossing   (A4)
-//   4. faces are binned by the (y,z) lattice cells their bounding box overlaps
-//   5. phi = min point-triangle distance for every voxel that is both marked and inside,
-//      searching lattice rings outwards until the ring's lower bound exceeds the best
-//   6. trilinear sampling with grid_sample(align_corners=False, zeros) semantics, its
+//      (y,z) lattice of +x rays; a hit toggles the bits of all voxels left of the crossing (A4)
+//   4. phi = min point-triangle distance for every voxel that is both marked and inside:
+//      face-centric — each face enumerates the marked voxels within R of its bounding box,
+//      (voxel, face) candidates are queued and the exact tests run densely, one per thread;
+//      voxels whose nearest face is beyond R are finished by a warp-wide search over static
+//      face clusters (nearest bounding box first)
+//   5. trilinear sampling with grid_sample(align_corners=False, zeros) semantics, its
 //      gradient w.r.t. the query vertex, per-frame loss = sum / 4                 (A3, A5, A6)
 //
 // The voxel values are exactly those of the brute-force 32^3 grid of the reference kernel
@@ -22,31 +24,33 @@ namespace ihmr {
 
 constexpr int G = 32;
 constexpr int SDF_THREADS = 256;
+constexpr int SDF_WARPS = SDF_THREADS / 32;
 constexpr int SDF_SLOTS = 4;        // 4 x 256 >= 778 query vertices
 constexpr int PHI_CAP = 4096;       // voxels evaluated per pass
-constexpr int BIN_CAP = 6144;       // (face, lattice cell) pairs
+constexpr int Q_CAP = 4096;         // queued (voxel, face) candidates
 constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
-constexpr int SDF_MAX_RING = 2;     // lattice rings searched per voxel before the cluster search takes over
+constexpr int P_CAP = 2048;         // queued (voxel, cluster) pairs of one distance band
+constexpr float SDF_R = 2.5f * (2.0f / G);   // candidate radius of the face-centric pass (2.5 voxels)
+constexpr float SDF_R2 = SDF_R * SDF_R;
 
 struct __align__(16) SdfSmem {
-    float U[NV * 3];
-    uint32_t needed[G * G];     // marked voxels per (z,y) column; later bin counters/cursors
+    float U[NV * 3];            // normalised grid-hand vertices
+    uint32_t needed[G * G];     // marked voxels per (z,y) column
     uint32_t work[G * G];       // parity bits, then marked & inside
+    uint32_t row_mask[G];       // bit j of row k: column (k,j) holds a marked & inside voxel
     uint16_t coloff[G * G];     // exclusive prefix of popc(work)
-    uint16_t bin_start[G * G + 2];
-    uint16_t bin_entries[BIN_CAP];
-    uint16_t worklist[PHI_CAP];
-    uint16_t far_list[PHI_CAP]; // voxels whose nearest face is beyond the ring search
-    float phi[PHI_CAP];
+    uint16_t worklist[PHI_CAP]; // (column << 5) | x of the voxels of the current pass
+    uint16_t far_list[PHI_CAP]; // voxels whose nearest face is beyond SDF_R
+    uint32_t best[PHI_CAP];     // bit pattern of the best squared distance (>= 0: orders like uint); then phi
+    uint32_t queue[Q_CAP];      // (voxel index << 16) | slot of the face in the cluster table
     float cl_box[NCL * 6];      // bounding boxes of the static face clusters (lo xyz, hi xyz)
-    uint32_t col_mask[G];       // lattice columns that hold a marked & inside voxel
-    uint32_t near_mask[G];      // ... dilated by SDF_MAX_RING columns
     float red[64];
     float box[2][2][3];         // [hand][lo/hi][xyz]
     float shift[4];
-    int scan_warp[8];
+    int scan_warp[SDF_WARPS];
+    uint32_t qn;
+    uint32_t pn[4];
     int far_count;
-    int scalars[3];
 };
 
 __device__ __forceinline__ float voxel_center(int i) { return (2.0f * i + 1.0f - G) / G; }
@@ -94,21 +98,21 @@ __device__ __forceinline__ float pt_tri_dist2(const float* p, const float* a, co
     if (d6 >= 0.f && d5 <= d6) return dot3(cp, cp);
     const float vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
     if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
-        const float t = d1 / (d1 - d3);
+        const float t = __fdividef(d1, d1 - d3);
 #pragma unroll
         for (int k = 0; k < 3; ++k) cl[k] = a[k] + t * ab[k];
     } else if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
-        const float t = d2 / (d2 - d6);
+        const float t = __fdividef(d2, d2 - d6);
 #pragma unroll
         for (int k = 0; k < 3; ++k) cl[k] = a[k] + t * ac[k];
     } else if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
-        const float t = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        const float t = __fdividef(d4 - d3, (d4 - d3) + (d5 - d6));
 #pragma unroll
         for (int k = 0; k < 3; ++k) cl[k] = b[k] + t * (c[k] - b[k]);
     } else {
         const float den = va + vb + vc;
         if (den == 0.f) return fminf(dot3(ap, ap), fminf(dot3(bp, bp), dot3(cp, cp)));
-        const float v = vb / den, w = vc / den;
+        const float rden = __fdividef(1.0f, den), v = vb * rden, w = vc * rden;
 #pragma unroll
         for (int k = 0; k < 3; ++k) cl[k] = a[k] + v * ab[k] + w * ac[k];
     }
@@ -123,6 +127,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // deterministic block sum of up to 4 values per thread; result valid in every thread
 __device__ __forceinline__ void block_sum4(float* v, int nval, float* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -134,7 +144,7 @@ __device__ __forceinline__ void block_sum4(float* v, int nval, float* red) {
     for (int i = 0; i < nval; ++i) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < SDF_THREADS / 32; ++w) s += red[i * 8 + w];
+        for (int w = 0; w < SDF_WARPS; ++w) s += red[i * 8 + w];
         v[i] = s;
     }
     __syncthreads();
@@ -154,7 +164,7 @@ __device__ __forceinline__ int block_scan_1024(const int (&cnt)[4], int (&excl)[
     __syncthreads();
     int base = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < SDF_THREADS / 32; ++w) {
+    for (int w = 0; w < SDF_WARPS; ++w) {
         if (w < warp) base += scan_warp[w];
         total += scan_warp[w];
     }
@@ -165,100 +175,28 @@ __device__ __forceinline__ int block_scan_1024(const int (&cnt)[4], int (&excl)[
     return total;
 }
 
-__device__ __forceinline__ int lattice_cell(float y) {   // cell of width 2/G centred on a voxel centre
-    int c = (int)floorf((y + 1.0f) * (0.5f * G));
-    return min(G - 1, max(0, c));
+__device__ __forceinline__ void voxel_pos(int code, float* q) {
+    q[0] = voxel_center(code & 31); q[1] = voxel_center((code >> 5) & 31); q[2] = voxel_center(code >> 10);
 }
 
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// ((SDF_MAX_RING + 0.5) cells)^2: a voxel whose nearest face is farther cannot be finished by the ring search
-constexpr float SDF_NEAR_LIMIT2 = ((SDF_MAX_RING + 0.5f) * (2.0f / G)) * ((SDF_MAX_RING + 0.5f) * (2.0f / G));
-
-// lower bound of the squared distance from a voxel to the mesh: nearest cluster bounding box
-// (the 8 lanes of an octet split the clusters; all 32 lanes must call this)
-__device__ __forceinline__ float cluster_lower_bound_octet(const SdfSmem& s, int code, int gl) {
-    const int x = code & 31, col = code >> 5, j = col & 31, k = col >> 5;
-    const float q[3] = {voxel_center(x), voxel_center(j), voxel_center(k)};
-    float lb = 1e30f;
-    for (int c = gl; c < NCL; c += 8) {
-        const float* bx = s.cl_box + c * 6;
-        float d2 = 0.f;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float d = fmaxf(fmaxf(bx[a] - q[a], q[a] - bx[3 + a]), 0.f);
-            d2 += d * d;
-        }
-        lb = fminf(lb, d2);
-    }
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) lb = fminf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
-    return lb;
-}
-
-// Squared distance from voxel `code` to the nearest face found in the lattice bins within
-// SDF_MAX_RING rings of its (y,z) column, computed by an OCTET (8 consecutive lanes) per voxel.
-// `done` tells whether the result is certified: a face not binned within ring r has every point
-// farther than (r + 0.5) cells away, so best <= ((SDF_MAX_RING + 0.5) cells)^2 is the exact
-// minimum over ALL faces.  Own column first (it holds the faces the voxel's x-ray crosses, a
-// good upper bound), then the 24 neighbour columns with two cheap rejections: the column's
-// (y,z) offset and the face's x-extent.  All 32 lanes must call this (shuffles).
-__device__ __forceinline__ float eval_voxel_near(const SdfSmem& s, const uint16_t* __restrict__ faces, int code,
-                                                 bool valid, int lane, bool& done) {
-    const int gl = lane & 7;
-    const int x = code & 31, col = code >> 5, j = col & 31, k = col >> 5;
-    const float q[3] = {voxel_center(x), voxel_center(j), voxel_center(k)};
-    const ushort4* f4 = reinterpret_cast<const ushort4*>(faces);
-    const float h = 2.0f / G;
-    float best = 1e30f;
-    if (valid) {
-        for (int e = s.bin_start[col] + gl; e < s.bin_start[col + 1]; e += 8) {
-            const ushort4 id = f4[s.bin_entries[e]];
-            best = fminf(best, pt_tri_dist2(q, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z));
-        }
-    }
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (valid) {
-        constexpr int W = 2 * SDF_MAX_RING + 1;
-        for (int n = gl; n < W * W; n += 8) {
-            const int dj = n % W - SDF_MAX_RING, dk = n / W - SDF_MAX_RING;
-            if (dj == 0 && dk == 0) continue;
-            const int jj = j + dj, kk = k + dk;
-            if (jj < 0 || jj >= G || kk < 0 || kk >= G) continue;
-            // every point of a face binned only here is at least this far away in (y,z)
-            const float oy = fmaxf(fabsf((float)dj) - 0.5f, 0.f) * h, oz = fmaxf(fabsf((float)dk) - 0.5f, 0.f) * h;
-            const float yz2 = oy * oy + oz * oz;
-            if (yz2 >= best) continue;
-            const int c = kk * G + jj;
-            for (int e = s.bin_start[c]; e < s.bin_start[c + 1]; ++e) {
-                const ushort4 id = f4[s.bin_entries[e]];
-                const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
-                const float dx = fmaxf(fmaxf(fminf(A_[0], fminf(B_[0], C_[0])) - q[0], q[0] - fmaxf(A_[0], fmaxf(B_[0], C_[0]))), 0.f);
-                if (dx * dx >= best) continue;       // x-extent alone is already too far
-                best = fminf(best, pt_tri_dist2(q, A_, B_, C_));
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    done = best <= SDF_NEAR_LIMIT2 - 1e-6f;
-    return best;
+// one exact (voxel, face) test; the result lowers the voxel's best squared distance
+__device__ __forceinline__ void pair_test(SdfSmem& s, const ushort4* __restrict__ cl_tri, int vi, int slot) {
+    float q[3];
+    voxel_pos(s.worklist[vi], q);
+    const ushort4 id = cl_tri[slot];
+    const float d2 = pt_tri_dist2(q, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z);
+    atomicMin(&s.best[vi], __float_as_uint(d2));
 }
 
 // Exact squared distance for a far voxel, one warp per voxel: the faces are grouped at model
 // creation into NCL spatial clusters of <= 32 (cl_tri); clusters are visited nearest bounding
 // box first, one face per lane, until the nearest unvisited box is farther than the best
-// distance.  The open wrist makes some far-away voxels "inside" (odd crossing parity), and
-// the reference's brute-force loop gives them their true distance, so they must be exact too.
+// distance.  The open wrist makes some far-away voxels "inside" (odd crossing parity), and the
+// reference's brute-force loop gives them their true distance, so they must be exact too.
 __device__ __forceinline__ float eval_voxel_far(const SdfSmem& s, const ushort4* __restrict__ cl_tri, int code,
                                                 float best, int lane) {
-    const int x = code & 31, col = code >> 5, j = col & 31, k = col >> 5;
-    const float q[3] = {voxel_center(x), voxel_center(j), voxel_center(k)};
+    float q[3];
+    voxel_pos(code, q);
     float lb[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -295,12 +233,19 @@ __device__ __forceinline__ float eval_voxel_far(const SdfSmem& s, const ushort4*
     return best;
 }
 
+#define SDF_STAT(i)                                                                       \
+    if (a.stats && tid == 0) {                                                            \
+        const long long t_now = clock64();                                                \
+        a.stats[b * 32 + 8 + (i)] += (int)(t_now - t_prev);                               \
+        t_prev = t_now;                                                                   \
+    }
+
 __global__ void __launch_bounds__(SDF_THREADS)
 k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __restrict__ faces_l,
       const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SdfSmem& s = *reinterpret_cast<SdfSmem*>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
     const bool xform = (a.joints != nullptr);
 
@@ -323,6 +268,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
         if (xform && hand == 1) { out[0] = -out[0] + shx; out[1] += shy; out[2] += shz; }
     };
+    long long t_prev = clock64();
 
     // ---- bounding boxes of both hands
     {
@@ -340,7 +286,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 for (int c = 0; c < 3; ++c) { lo[hnd][c] = fminf(lo[hnd][c], p[c]); hi[hnd][c] = fmaxf(hi[hnd][c], p[c]); }
             }
         }
-        const int lane = tid & 31, warp = tid >> 5;
+        float* scratch = reinterpret_cast<float*>(s.queue);
 #pragma unroll
         for (int hnd = 0; hnd < 2; ++hnd)
 #pragma unroll
@@ -351,17 +297,18 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
                     hgh = fmaxf(hgh, __shfl_xor_sync(0xffffffffu, hgh, o));
                 }
-                if (lane == 0) { s.phi[(hnd * 3 + c) * 16 + warp] = l; s.phi[(hnd * 3 + c) * 16 + 8 + warp] = hgh; }
+                if (lane == 0) { scratch[(hnd * 3 + c) * 16 + warp] = l; scratch[(hnd * 3 + c) * 16 + 8 + warp] = hgh; }
             }
         __syncthreads();
         if (tid < 6) {
             float l = 1e30f, hgh = -1e30f;
-            for (int w = 0; w < SDF_THREADS / 32; ++w) { l = fminf(l, s.phi[tid * 16 + w]); hgh = fmaxf(hgh, s.phi[tid * 16 + 8 + w]); }
+            for (int w = 0; w < SDF_WARPS; ++w) { l = fminf(l, scratch[tid * 16 + w]); hgh = fmaxf(hgh, scratch[tid * 16 + 8 + w]); }
             s.box[tid / 3][0][tid % 3] = l;
             s.box[tid / 3][1][tid % 3] = hgh;
         }
         __syncthreads();
     }
+    SDF_STAT(1)
 
     float mask = 1.0f;
     if (a.hand_type) mask = (a.hand_type[b * 2] + a.hand_type[b * 2 + 1] > 1.5f) ? 1.0f : 0.0f;
@@ -369,7 +316,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
 
     for (int h = 0; h < 2; ++h) {
         const int o = 1 - h;
-        const uint16_t* faces = h ? faces_l : faces_r;
+        const ushort4* f4 = reinterpret_cast<const ushort4*>(h ? faces_l : faces_r);
         const ushort4* cl_tri = h ? cl_l : cl_r;
         float cen[3], ext = 0.f;
 #pragma unroll
@@ -378,8 +325,15 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             ext = fmaxf(ext, s.box[h][1][c] - s.box[h][0][c]);
         }
         const float scale = 0.6f * ext;      // (1 + 0.2) * 0.5 * max extent
+        float tlo[3], thi[3];                // normalised extent of the grid hand itself (+ rounding slack)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            tlo[c] = (s.box[h][0][c] - cen[c]) / scale - 1e-4f;
+            thi[c] = (s.box[h][1][c] - cen[c]) / scale + 1e-4f;
+        }
 
         for (int i = tid; i < G * G; i += SDF_THREADS) { s.needed[i] = 0u; s.work[i] = 0u; }
+        if (tid < G) s.row_mask[tid] = 0u;
         __syncthreads();
 
         // ---- query vertices: normalised position, voxel corners, mark
@@ -410,26 +364,34 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 }
                 act[sl] = in;
                 if (in) {
-                    any = true;
+                    // A voxel can only be inside (odd +x crossings) if its (y,z) lies within the
+                    // mesh's (y,z) extent and its x is left of the mesh's largest x: other corners
+                    // are certainly 0 and need not be marked.
 #pragma unroll
                     for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy) {
                             const int zc = i0[sl][2] + dz, yc = i0[sl][1] + dy;
                             if (zc < 0 || zc >= G || yc < 0 || yc >= G) continue;
+                            const float yv = voxel_center(yc), zv = voxel_center(zc);
+                            if (yv < tlo[1] || yv > thi[1] || zv < tlo[2] || zv > thi[2]) continue;
                             uint32_t bits = 0u;
-                            if (i0[sl][0] >= 0) bits |= 1u << i0[sl][0];
-                            if (i0[sl][0] + 1 < G) bits |= 1u << (i0[sl][0] + 1);
-                            atomicOr(&s.needed[zc * G + yc], bits);
+                            if (i0[sl][0] >= 0 && voxel_center(i0[sl][0]) <= thi[0]) bits |= 1u << i0[sl][0];
+                            if (i0[sl][0] + 1 < G && voxel_center(i0[sl][0] + 1) <= thi[0]) bits |= 1u << (i0[sl][0] + 1);
+                            if (bits) { any = true; atomicOr(&s.needed[zc * G + yc], bits); }
                         }
                 }
             }
         }
         const bool any_block = __syncthreads_or(any);
-        if (a.stats) { const int nact = __syncthreads_count(act[0]) + __syncthreads_count(act[1]) + __syncthreads_count(act[2]) + __syncthreads_count(act[3]); if (tid == 0) a.stats[b * 8 + 4 + h] = nact; }
+        if (a.stats) {
+            const int nact = __syncthreads_count(act[0]) + __syncthreads_count(act[1]) + __syncthreads_count(act[2]) +
+                             __syncthreads_count(act[3]);
+            if (tid == 0) a.stats[b * 32 + 4 + h] = nact;
+        }
+        SDF_STAT(2)
         bool run = any_block;
         int total = 0;
-        bool use_bins = true;
 
         if (run) {
             // ---- normalised grid-hand vertices
@@ -440,9 +402,10 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 for (int c = 0; c < 3; ++c) s.U[v * 3 + c] = (p[c] - cen[c]) / scale;
             }
             __syncthreads();
+            SDF_STAT(3)
             // ---- parity of the marked columns
             for (int f = tid; f < NF; f += SDF_THREADS) {
-                const ushort4 id = reinterpret_cast<const ushort4*>(faces)[f];
+                const ushort4 id = f4[f];
                 const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
                 const float ymin = fminf(A_[1], fminf(B_[1], C_[1])), ymax = fmaxf(A_[1], fmaxf(B_[1], C_[1]));
                 const float zmin = fminf(A_[2], fminf(B_[2], C_[2])), zmax = fmaxf(A_[2], fmaxf(B_[2], C_[2]));
@@ -464,7 +427,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     }
             }
             __syncthreads();
-            // ---- marked & inside, prefix offsets
+            SDF_STAT(4)
+            // ---- marked & inside, prefix offsets, per-row column masks
             int cnt[4], excl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -472,96 +436,19 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 const uint32_t wk = s.needed[c] & s.work[c];
                 s.work[c] = wk;
                 cnt[i] = __popc(wk);
+                if (wk) atomicOr(&s.row_mask[c >> 5], 1u << (c & 31));
             }
             total = block_scan_1024(cnt, excl, s.scan_warp);
 #pragma unroll
             for (int i = 0; i < 4; ++i) s.coloff[tid * 4 + i] = (uint16_t)excl[i];
             run = total > 0;
+            SDF_STAT(5)
         }
         if (run) {
-            // ---- lattice columns that can be reached by a ring search: work columns dilated by SDF_MAX_RING
-            if (tid < G) s.col_mask[tid] = 0u;
-            for (int i = tid; i < G * G; i += SDF_THREADS) s.needed[i] = 0u;   // needed[] is free now: bin counters/cursors
-            __syncthreads();
-            for (int i = tid; i < G * G; i += SDF_THREADS)
-                if (s.work[i]) atomicOr(&s.col_mask[i >> 5], 1u << (i & 31));
-            __syncthreads();
-            if (tid < G) {
-                uint32_t m = 0u;
-                for (int kk = max(0, tid - SDF_MAX_RING); kk <= min(G - 1, tid + SDF_MAX_RING); ++kk) m |= s.col_mask[kk];
-                uint32_t d = m;
-#pragma unroll
-                for (int r = 1; r <= SDF_MAX_RING; ++r) d |= (m << r) | (m >> r);
-                s.near_mask[tid] = d;
-            }
-            __syncthreads();
-            // ---- bin faces by the lattice cells their bounding box overlaps (reachable cells only)
-            for (int f = tid; f < NF; f += SDF_THREADS) {
-                const ushort4 id = reinterpret_cast<const ushort4*>(faces)[f];
-                const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
-                const int j0 = lattice_cell(fminf(A_[1], fminf(B_[1], C_[1]))), j1 = lattice_cell(fmaxf(A_[1], fmaxf(B_[1], C_[1])));
-                const int k0 = lattice_cell(fminf(A_[2], fminf(B_[2], C_[2]))), k1 = lattice_cell(fmaxf(A_[2], fmaxf(B_[2], C_[2])));
-                for (int k = k0; k <= k1; ++k)
-                    for (int j = j0; j <= j1; ++j)
-                        if ((s.near_mask[k] >> j) & 1u) atomicAdd(&s.needed[k * G + j], 1u);
-            }
-            __syncthreads();
-            int cnt[4], excl[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cnt[i] = (int)s.needed[tid * 4 + i];
-            const int entries = block_scan_1024(cnt, excl, s.scan_warp);
-            use_bins = entries <= BIN_CAP;
-            if (a.stats && tid == 0) a.stats[b * 8 + 6 + h] = entries;
-            if (use_bins) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { s.bin_start[tid * 4 + i] = (uint16_t)excl[i]; s.needed[tid * 4 + i] = 0u; }
-                if (tid == 0) s.bin_start[G * G] = (uint16_t)entries;
-                __syncthreads();
-                for (int f = tid; f < NF; f += SDF_THREADS) {
-                    const ushort4 id = reinterpret_cast<const ushort4*>(faces)[f];
-                    const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
-                    const int j0 = lattice_cell(fminf(A_[1], fminf(B_[1], C_[1]))), j1 = lattice_cell(fmaxf(A_[1], fmaxf(B_[1], C_[1])));
-                    const int k0 = lattice_cell(fminf(A_[2], fminf(B_[2], C_[2]))), k1 = lattice_cell(fmaxf(A_[2], fmaxf(B_[2], C_[2])));
-                    for (int k = k0; k <= k1; ++k)
-                        for (int j = j0; j <= j1; ++j) {
-                            if (!((s.near_mask[k] >> j) & 1u)) continue;
-                            const int c = k * G + j;
-                            const uint32_t pos = s.bin_start[c] + atomicAdd(&s.needed[c], 1u);
-                            s.bin_entries[pos] = (uint16_t)f;
-                        }
-                }
-            }
-            // ---- bounding boxes of the static face clusters (used by the far search)
-            for (int c = tid >> 5; c < NCL; c += SDF_THREADS / 32) {
-                const ushort4 id = cl_tri[c * 32 + (tid & 31)];
-                float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-                if (id.w) {
-                    const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
-#pragma unroll
-                    for (int ax = 0; ax < 3; ++ax) {
-                        lo[ax] = fminf(A_[ax], fminf(B_[ax], C_[ax]));
-                        hi[ax] = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
-                    }
-                }
-#pragma unroll
-                for (int ax = 0; ax < 3; ++ax) {
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) {
-                        lo[ax] = fminf(lo[ax], __shfl_xor_sync(0xffffffffu, lo[ax], o));
-                        hi[ax] = fmaxf(hi[ax], __shfl_xor_sync(0xffffffffu, hi[ax], o));
-                    }
-                }
-                if ((tid & 31) == 0) {
-#pragma unroll
-                    for (int ax = 0; ax < 3; ++ax) { s.cl_box[c * 6 + ax] = lo[ax]; s.cl_box[c * 6 + 3 + ax] = hi[ax]; }
-                }
-            }
-            if (tid == 0) s.far_count = 0;
-            __syncthreads();
-
             // ---- passes over the marked & inside voxels
             for (int pass0 = 0; pass0 < total; pass0 += PHI_CAP) {
                 const int pass1 = min(total, pass0 + PHI_CAP);
+                const int nvox = pass1 - pass0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = tid * 4 + i;
@@ -574,32 +461,128 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                         ++idx;
                     }
                 }
+                for (int i = tid; i < nvox; i += SDF_THREADS) s.best[i] = 0x7f7fffffu;
+                if (tid == 0) { s.qn = 0u; s.far_count = 0; }
                 __syncthreads();
-                // near voxels: one octet of lanes each, ring search over the bins; the rest go to far_list
-                for (int i0v = (tid >> 5) * 4; i0v < pass1 - pass0; i0v += (SDF_THREADS / 32) * 4) {
-                    const int i = i0v + ((tid & 31) >> 3);
-                    const bool valid = i < pass1 - pass0;
-                    const int code = valid ? s.worklist[i] : 0;
-                    // voxels farther than the ring search can certify go straight to the far list
-                    const float lb_cl = cluster_lower_bound_octet(s, code, tid & 7);   // shuffles: every lane calls
-                    const bool near_ok = valid && use_bins && lb_cl <= SDF_NEAR_LIMIT2;
-                    bool done = false;
-                    const float best = eval_voxel_near(s, faces, code, near_ok, tid & 31, done);
-                    if (valid && (tid & 7) == 0) {
-                        if (near_ok && done) s.phi[i] = sqrtf(best);
-                        else { s.phi[i] = best; s.far_list[atomicAdd(&s.far_count, 1)] = (uint16_t)i; }
+                SDF_STAT(6)
+                // ---- nearest face of every voxel, bulk-synchronous and balanced:
+                //   (0) bounding boxes of the static face clusters (<= 32 faces each, spatially sorted)
+                //   for each distance band (< 0.5, < 1.25, < 2.5 voxels), nearest first:
+                //   (A) one thread per (voxel, cluster): box distance inside the band and below the
+                //       voxel's best -> (voxel, cluster) pairs; voxels already final are skipped
+                //   (B) one thread per (pair, face of the cluster): face-box distance against R and the
+                //       voxel's best so far -> (voxel, face) candidates
+                //   (C) one thread per candidate: exact point-triangle test, atomicMin into the voxel
+                //   Processing the bands in order makes (B) reject most faces of the outer bands.
+                for (int c = warp; c < NCL; c += SDF_WARPS) {
+                    const ushort4 id = cl_tri[c * 32 + lane];
+                    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+                    if (id.w) {
+                        const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) {
+                            lo[ax] = fminf(A_[ax], fminf(B_[ax], C_[ax]));
+                            hi[ax] = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
+                        }
                     }
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+                            lo[ax] = fminf(lo[ax], __shfl_xor_sync(0xffffffffu, lo[ax], sft));
+                            hi[ax] = fmaxf(hi[ax], __shfl_xor_sync(0xffffffffu, hi[ax], sft));
+                        }
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) { s.cl_box[c * 6 + ax] = lo[ax]; s.cl_box[c * 6 + 3 + ax] = hi[ax]; }
+                    }
+                }
+                if (tid < 4) s.pn[tid] = 0u;
+                __syncthreads();
+                uint32_t* pairs = reinterpret_cast<uint32_t*>(s.far_list);      // far_list is free until the classification
+                static_assert(sizeof(s.far_list) >= P_CAP * sizeof(uint32_t), "pair queue aliases far_list");
+                constexpr float cell = 2.0f / G;
+                const float band_hi[3] = {(0.5f * cell) * (0.5f * cell), (1.25f * cell) * (1.25f * cell), SDF_R2};
+                for (int band = 0; band < 3; ++band) {
+                    const float b_lo = band ? band_hi[band - 1] : 0.f, b_hi = band_hi[band];
+                    // (A) voxel x cluster.  A voxel whose best is below the previous band limit is final:
+                    //     every face closer than that limit sits in a cluster that was already processed.
+                    for (int i = tid; i < nvox * NCL; i += SDF_THREADS) {
+                        const int v = i / NCL, c = i - v * NCL;
+                        const float bv = __uint_as_float(s.best[v]);
+                        if (bv < b_lo) continue;
+                        float q[3];
+                        voxel_pos(s.worklist[v], q);
+                        const float* bx = s.cl_box + c * 6;
+                        float d2 = 0.f;
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) {
+                            const float d = fmaxf(fmaxf(bx[ax] - q[ax], q[ax] - bx[3 + ax]), 0.f);
+                            d2 += d * d;
+                        }
+                        if (d2 < b_lo || d2 >= b_hi || d2 >= bv) continue;
+                        const uint32_t pos = atomicAdd(&s.pn[0], 1u);
+                        if (pos < P_CAP) pairs[pos] = ((uint32_t)v << 6) | (uint32_t)c;
+                        else {
+                            // pair queue full (very many marked voxels): this thread handles the cluster itself
+                            for (int l = 0; l < 32; ++l) {
+                                const ushort4 id = cl_tri[c * 32 + l];
+                                if (id.w) pair_test(s, cl_tri, v, c * 32 + l);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // (B) pair x face of the cluster
+                    const int np = min((int)s.pn[0], P_CAP);
+                    for (int jj = tid; jj < np * 32; jj += SDF_THREADS) {
+                        const uint32_t pr = pairs[jj >> 5];
+                        const int v = pr >> 6, slot = (pr & 63u) * 32 + (jj & 31);
+                        const ushort4 id = cl_tri[slot];
+                        if (!id.w) continue;
+                        float q[3];
+                        voxel_pos(s.worklist[v], q);
+                        const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
+                        float d2 = 0.f;
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) {
+                            const float lo = fminf(A_[ax], fminf(B_[ax], C_[ax])), hi = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
+                            const float d = fmaxf(fmaxf(lo - q[ax], q[ax] - hi), 0.f);
+                            d2 += d * d;
+                        }
+                        // a face whose box is farther than R or than the voxel's best cannot matter
+                        if (d2 >= SDF_R2 || d2 >= __uint_as_float(s.best[v])) continue;
+                        const uint32_t pos = atomicAdd(&s.qn, 1u);
+                        if (pos < Q_CAP) s.queue[pos] = ((uint32_t)v << 16) | (uint32_t)slot;
+                        else pair_test(s, cl_tri, v, slot);          // queue full: test in place
+                    }
+                    __syncthreads();
+                    // (C) exact tests
+                    const int nq = min((int)s.qn, Q_CAP);
+                    for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) pair_test(s, cl_tri, s.queue[p2] >> 16, s.queue[p2] & 0xffffu);
+                    __syncthreads();
+                    if (tid == 0) { s.qn = 0u; s.pn[0] = 0u; }
+                    __syncthreads();
+                }
+                SDF_STAT(7)
+                // ---- certified voxels get phi; the others (nearest face beyond R) go to the far search
+                for (int i = tid; i < nvox; i += SDF_THREADS) {
+                    const float d2 = __uint_as_float(s.best[i]);
+                    if (d2 < SDF_R2 * 0.9999f) s.best[i] = __float_as_uint(sqrtf(d2));
+                    else s.far_list[atomicAdd(&s.far_count, 1)] = (uint16_t)i;
                 }
                 __syncthreads();
                 const int nfar = s.far_count;
-                if (a.stats && tid == 0) { a.stats[b * 8 + 2 * h] += pass1 - pass0; a.stats[b * 8 + 2 * h + 1] += nfar; }
-                for (int w = tid >> 5; w < nfar; w += SDF_THREADS / 32) {
-                    const int i = s.far_list[w];
-                    const float best = eval_voxel_far(s, cl_tri, s.worklist[i], s.phi[i], tid & 31);
-                    if ((tid & 31) == 0) s.phi[i] = sqrtf(best);
+                if (a.stats && tid == 0) { a.stats[b * 32 + 2 * h] += nvox; a.stats[b * 32 + 2 * h + 1] += nfar; }
+                if (nfar > 0) {
+                    for (int w = warp; w < nfar; w += SDF_WARPS) {
+                        const int i = s.far_list[w];
+                        const float d2 = eval_voxel_far(s, cl_tri, s.worklist[i], __uint_as_float(s.best[i]), lane);
+                        if (lane == 0) s.best[i] = __float_as_uint(sqrtf(d2));
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
-                if (tid == 0) s.far_count = 0;
+                SDF_STAT(8)
                 // ---- trilinear sample + gradient (grid_sampler_3d fwd/bwd, align_corners=False, zeros)
 #pragma unroll
                 for (int sl = 0; sl < SDF_SLOTS; ++sl) {
@@ -618,7 +601,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                                 if (!((wk >> xc) & 1u)) continue;
                                 const int idx = s.coloff[c] + __popc(wk & ((1u << xc) - 1u));
                                 if (idx < pass0 || idx >= pass1) continue;
-                                const float val = s.phi[idx - pass0];
+                                const float val = __uint_as_float(s.best[idx - pass0]);
                                 const float wx = dx ? tx : 1.0f - tx, wy = dy ? ty : 1.0f - ty, wz = dz ? tz : 1.0f - tz;
                                 acc[sl][0] += val * wx * wy * wz;
                                 acc[sl][1] += (dx ? val : -val) * wy * wz;
@@ -627,6 +610,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                             }
                 }
                 __syncthreads();
+                SDF_STAT(9)
             }
         }
 
@@ -649,8 +633,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             if (a.origin) a.origin[ov] = psi * scale;
             if (a.gverts) {
                 // d psi / d vertex = (G/2) * d psi / d(ix) / scale ; loss = sum(rho) / 4
-                const float k = mask * a.grad_scale * 0.25f * drho * (0.5f * G) / scale;
-                float g[3] = {k * acc[sl][1], k * acc[sl][2], k * acc[sl][3]};
+                const float kk = mask * a.grad_scale * 0.25f * drho * (0.5f * G) / scale;
+                float g[3] = {kk * acc[sl][1], kk * acc[sl][2], kk * acc[sl][3]};
                 gsum[0] += g[0]; gsum[1] += g[1]; gsum[2] += g[2];
                 if (xform && o == 1) g[0] = -g[0];
                 float* gp = a.gverts + ov * 3;
@@ -662,6 +646,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             if (tid < 3) a.gshift[(size_t)b * 3 + tid] = gsum[tid];
         }
         __syncthreads();
+        SDF_STAT(10)
     }
     float lp[1] = {loss_part};
     block_sum4(lp, 1, s.red);

@@ -92,9 +92,10 @@ int ihmr_sdf_loss(const ihmr_model_t* model, int n_frames, const float* hand_ver
                   float* per_vert, float* origin_scale, float* grad_hand_verts, float robustifier,
                   ihmr_stream_t stream);
 
-/* Diagnostic variant for tools/tests: same kernel, additionally fills stats (n,8) int32 (zeroed
+/* Diagnostic variant for tools/tests: same kernel, additionally fills stats (n,32) int32 (zeroed
  * by the caller): per grid hand h in {0,1}: [2h] voxels evaluated, [2h+1] of them by the far
- * (cluster) search, [4+h] query vertices inside the grid box, [6+h] (face, lattice cell) pairs. */
+ * (cluster) search, [4+h] query vertices inside the grid box, [9..18] SM cycles thread 0 spent per kernel phase (bbox,
+ * mark, normalise, parity, scan, worklist, candidates+tests, classify+far, sample, outputs). */
 int ihmr_sdf_stats(const ihmr_model_t* model, int n_frames, const float* hand_verts, float* losses,
                    int32_t* stats, ihmr_stream_t stream);
 

@@ -16,7 +16,7 @@ model = OptimizeModel(H.make_opt(root, args.frames, strategy=with_epochs(opt_def
 raw = synthetic.make_raw_frames(0, args.frames, seed=0, mode=args.mode)
 model.set_input(H.torch_batch(gpu_targets(model, raw, dev))); model.init_optimize(); model.forward()
 hv = torch.stack([model.pred_right_hand_verts, model.pred_left_hand_verts], 1).contiguous()
-losses = torch.empty(args.frames, device=dev); stats = torch.zeros(args.frames, 8, dtype=torch.int32, device=dev)
+losses = torch.empty(args.frames, device=dev); stats = torch.zeros(args.frames, 32, dtype=torch.int32, device=dev)
 lib = _lib.load()
 _lib.check(lib.ihmr_sdf_stats(model._model.handle, args.frames, C.c_void_p(hv.data_ptr()), C.c_void_p(losses.data_ptr()),
                               C.c_void_p(stats.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "stats")
@@ -26,4 +26,13 @@ names = ["evalR", "farR", "evalL", "farL", "activeQ(gridR)", "activeQ(gridL)", "
 for i, n in enumerate(names):
     c = st[:, i]
     print(f"{n:>16}: mean {c.mean():8.1f}  p50 {np.percentile(c,50):7.0f} p90 {np.percentile(c,90):7.0f} p99 {np.percentile(c,99):7.0f} max {c.max():7.0f}  nonzero {np.mean(c>0)*100:5.1f}%")
+for i, n in [(20, "visitsR"), (21, "visitsL"), (22, "testsR"), (23, "testsL")]:
+    c = st[:, i]
+    print(f"{n:>16}: mean {c.mean():9.1f}  p50 {np.percentile(c,50):7.0f} p90 {np.percentile(c,90):8.0f} p99 {np.percentile(c,99):8.0f} max {c.max():8.0f}")
+ph = ["-", "bbox", "mark", "normalise", "parity", "scan", "worklist", "candidates+tests", "classify+far", "sample", "outputs", "-"]
+tot = st[:, 8:20].sum()
+for i in range(1, 12):
+    c = st[:, 8 + i]
+    print(f"{ph[i]:>14}: {c.sum()/tot*100:5.1f}% of cycles  mean {c.mean():9.0f}  p99 {np.percentile(c,99):9.0f}  max {c.max():9.0f}")
+print("mean cycles per frame", st[:, 8:20].sum(1).mean())
 print("loss>0 frames %.1f%%, mean loss %.3f" % (np.mean(l > 0) * 100, l.mean()))
