@@ -64,6 +64,8 @@ struct SdfArgs {
     float* gshift = nullptr;           // (B,3) or null
     float grad_scale = 1.0f;           // gverts/gshift = grad_scale * d losses[b]/d(.)
     float robustifier = 0.0f;
+    int skip_grid_mask = 0;            // bit h: skip the direction whose grid hand is h (its loss part and
+                                       // the gradients of the other hand are then NOT produced)
     int* stats = nullptr;              // (B,32) debug counters / phase cycles (zeroed by the caller), tests/tools only
 };
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);

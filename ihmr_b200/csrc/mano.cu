@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(128) k_pose_bwd(int n, HandSrc src, const floa
         for (int k = 0; k < 3; ++k) dJ[k] += dtg[k];
     }
     // pose-feature gradient from the blend GEMM: f = vec(R_j - I), j >= 1
-    const float* dx = dX + (size_t)h * KP;
-    if (j >= 1) {
+    const float* dx = dX ? dX + (size_t)h * KP : nullptr;
+    if (dx && j >= 1) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) dR[i] += dx[(j - 1) * 9 + i];
     }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(int n, HandSrc src, const floa
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
-        db[k] = v + dx[NPF + k];
+        db[k] = v + (dx ? dx[NPF + k] : 0.f);
     }
     if (!active) return;
     if (FUSED) {

@@ -315,6 +315,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
     float loss_part = 0.f;
 
     for (int h = 0; h < 2; ++h) {
+        if ((a.skip_grid_mask >> h) & 1) continue;      // block-uniform: this direction is not needed
         const int o = 1 - h;
         const ushort4* f4 = reinterpret_cast<const ushort4*>(h ? faces_l : faces_r);
         const ushort4* cl_tri = h ? cl_l : cl_r;
@@ -631,14 +632,16 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             const size_t ov = (size_t)b * (2 * NV) + o * NV + v;
             if (a.per_vert) a.per_vert[ov] = rho;
             if (a.origin) a.origin[ov] = psi * scale;
-            if (a.gverts) {
+            if (a.gverts || a.gshift) {
                 // d psi / d vertex = (G/2) * d psi / d(ix) / scale ; loss = sum(rho) / 4
                 const float kk = mask * a.grad_scale * 0.25f * drho * (0.5f * G) / scale;
                 float g[3] = {kk * acc[sl][1], kk * acc[sl][2], kk * acc[sl][3]};
                 gsum[0] += g[0]; gsum[1] += g[1]; gsum[2] += g[2];
-                if (xform && o == 1) g[0] = -g[0];
-                float* gp = a.gverts + ov * 3;
-                gp[0] = g[0]; gp[1] = g[1]; gp[2] = g[2];
+                if (a.gverts) {
+                    if (xform && o == 1) g[0] = -g[0];
+                    float* gp = a.gverts + ov * 3;
+                    gp[0] = g[0]; gp[1] = g[1]; gp[2] = g[2];
+                }
             }
         }
         if (a.gshift && o == 1) {
