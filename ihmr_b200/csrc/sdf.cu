@@ -25,9 +25,12 @@ namespace ihmr {
 constexpr int G = 32;
 constexpr int SDF_THREADS = 256;
 constexpr int SDF_WARPS = SDF_THREADS / 32;
+#ifndef SDF_MIN_CTAS
+#define SDF_MIN_CTAS 3               // resident CTAs per SM the register allocation is held to
+#endif
 constexpr int SDF_SLOTS = 4;        // 4 x 256 >= 778 query vertices
-constexpr int PHI_CAP = 4096;       // voxels evaluated per pass
-constexpr int Q_CAP = 4096;         // queued (voxel, face) candidates
+constexpr int PHI_CAP = 4096;       // voxels evaluated per pass (more voxels: further passes)
+constexpr int Q_CAP = 2048;         // queued candidates (overflow is processed in place)
 constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
 constexpr int P_CAP = 2048;         // queued (voxel, cluster) pairs of one distance band
 constexpr float SDF_R = 2.5f * (2.0f / G);   // candidate radius of the face-centric pass (2.5 voxels)
@@ -44,6 +47,7 @@ struct __align__(16) SdfSmem {
     uint32_t best[PHI_CAP];     // bit pattern of the best squared distance (>= 0: orders like uint); then phi
     uint32_t queue[Q_CAP];      // (voxel index << 16) | slot of the face in the cluster table
     float cl_box[NCL * 6];      // bounding boxes of the static face clusters (lo xyz, hi xyz)
+    uint8_t fbox8[NCL * 32 * 6];// per face (cluster-table order): box quantised outwards to 1/127.5, lo xyz hi xyz
     float red[64];
     float box[2][2][3];         // [hand][lo/hi][xyz]
     float shift[4];
@@ -81,43 +85,37 @@ __device__ __forceinline__ bool ray_hit(const float* P, int ia, int ib, int ic, 
 
 __device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-// squared distance point -> triangle (closest-point regions)
+// Squared distance point -> triangle, branch free (all lanes of a warp stay converged):
+// min over the three edge segments and, when the projection falls inside, the plane distance.
+// Same quantities as the closest-point-region formulation of oracle/sdf_oracle.c (d1..d6,
+// va/vb/vc); agrees with it to rounding.  fminf/fmaxf drop NaNs, which makes zero-length edges
+// and zero-area faces fall back to the remaining candidates.
 __device__ __forceinline__ float pt_tri_dist2(const float* p, const float* a, const float* b, const float* c) {
-    float ab[3], ac[3], ap[3], bp[3], cp[3], cl[3];
+    float ab[3], ac[3], ap[3], bp[3], cp[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
-    const float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
-    if (d1 <= 0.f && d2 <= 0.f) return dot3(ap, ap);
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; bp[k] = p[k] - b[k]; cp[k] = p[k] - c[k]; }
+    const float d1 = dot3(ab, ap), d2 = dot3(ac, ap), d3 = dot3(ab, bp), d4 = dot3(ac, bp), d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    // edge ab: t = d1 / |ab|^2, |ab|^2 = d1 - d3
+    const float t1 = fminf(fmaxf(__fdividef(d1, d1 - d3), 0.f), 1.f);
+    float e[3] = {ap[0] - t1 * ab[0], ap[1] - t1 * ab[1], ap[2] - t1 * ab[2]};
+    float best = dot3(e, e);
+    // edge ac: t = d2 / |ac|^2, |ac|^2 = d2 - d6
+    const float t2 = fminf(fmaxf(__fdividef(d2, d2 - d6), 0.f), 1.f);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) bp[k] = p[k] - b[k];
-    const float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
-    if (d3 >= 0.f && d4 <= d3) return dot3(bp, bp);
+    for (int k = 0; k < 3; ++k) e[k] = ap[k] - t2 * ac[k];
+    best = fminf(best, dot3(e, e));
+    // edge bc: t = (d4 - d3) / |bc|^2, |bc|^2 = (d4 - d3) + (d5 - d6)
+    const float t3 = fminf(fmaxf(__fdividef(d4 - d3, (d4 - d3) + (d5 - d6)), 0.f), 1.f);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) cp[k] = p[k] - c[k];
-    const float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
-    if (d6 >= 0.f && d5 <= d6) return dot3(cp, cp);
+    for (int k = 0; k < 3; ++k) e[k] = bp[k] - t3 * (ac[k] - ab[k]);
+    best = fminf(best, dot3(e, e));
+    // interior: barycentric coordinates all non-negative
     const float vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
-    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
-        const float t = __fdividef(d1, d1 - d3);
+    const float rden = __fdividef(1.0f, va + vb + vc), v = vb * rden, w = vc * rden;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) cl[k] = a[k] + t * ab[k];
-    } else if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
-        const float t = __fdividef(d2, d2 - d6);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cl[k] = a[k] + t * ac[k];
-    } else if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
-        const float t = __fdividef(d4 - d3, (d4 - d3) + (d5 - d6));
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cl[k] = b[k] + t * (c[k] - b[k]);
-    } else {
-        const float den = va + vb + vc;
-        if (den == 0.f) return fminf(dot3(ap, ap), fminf(dot3(bp, bp), dot3(cp, cp)));
-        const float rden = __fdividef(1.0f, den), v = vb * rden, w = vc * rden;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cl[k] = a[k] + v * ab[k] + w * ac[k];
-    }
-    float d[3] = {p[0] - cl[0], p[1] - cl[1], p[2] - cl[2]};
-    return dot3(d, d);
+    for (int k = 0; k < 3; ++k) e[k] = ap[k] - v * ab[k] - w * ac[k];
+    const float din = dot3(e, e);
+    return (va >= 0.f && vb >= 0.f && vc >= 0.f) ? fminf(best, din) : best;
 }
 
 // ---- block primitives ---------------------------------------------------------------------
@@ -240,7 +238,7 @@ __device__ __forceinline__ float eval_voxel_far(const SdfSmem& s, const ushort4*
         t_prev = t_now;                                                                   \
     }
 
-__global__ void __launch_bounds__(SDF_THREADS)
+__global__ void __launch_bounds__(SDF_THREADS, SDF_MIN_CTAS)
 k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __restrict__ faces_l,
       const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -404,7 +402,21 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             }
             __syncthreads();
             SDF_STAT(3)
-            // ---- parity of the marked columns
+            // ---- parity of the marked columns, two steps so that the ray tests run with full warps:
+            //      (1) thread per face: lattice points inside its (y,z) box whose column is marked
+            //          -> (face, column) items; (2) thread per item: the exact ray test
+            if (tid == 0) s.qn = 0u;
+            __syncthreads();
+            auto ray_item = [&](int f, int col) {
+                const ushort4 id = f4[f];
+                float x;
+                if (!ray_hit(s.U, id.x, id.y, id.z, voxel_center(col & 31), voxel_center(col >> 5), x)) return;
+                // voxels whose centre lies strictly left of the crossing
+                int cnt = min(G, max(0, (int)ceilf((x * G + (G - 1)) * 0.5f)));
+                while (cnt < G && x > voxel_center(cnt)) ++cnt;
+                while (cnt > 0 && !(x > voxel_center(cnt - 1))) --cnt;
+                if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+            };
             for (int f = tid; f < NF; f += SDF_THREADS) {
                 const ushort4 id = f4[f];
                 const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
@@ -418,14 +430,15 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     for (int j = j0; j <= j1; ++j) {
                         const int col = k * G + j;
                         if (s.needed[col] == 0u) continue;
-                        float x;
-                        if (!ray_hit(s.U, id.x, id.y, id.z, voxel_center(j), voxel_center(k), x)) continue;
-                        // voxels whose centre lies strictly left of the crossing
-                        int cnt = min(G, max(0, (int)ceilf((x * G + (G - 1)) * 0.5f)));
-                        while (cnt < G && x > voxel_center(cnt)) ++cnt;
-                        while (cnt > 0 && !(x > voxel_center(cnt - 1))) --cnt;
-                        if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+                        const uint32_t pos = atomicAdd(&s.qn, 1u);
+                        if (pos < Q_CAP) s.queue[pos] = ((uint32_t)f << 10) | (uint32_t)col;
+                        else ray_item(f, col);
                     }
+            }
+            __syncthreads();
+            {
+                const int nq = min((int)s.qn, Q_CAP);
+                for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) ray_item(s.queue[p2] >> 10, s.queue[p2] & 1023u);
             }
             __syncthreads();
             SDF_STAT(4)
@@ -466,25 +479,32 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 if (tid == 0) { s.qn = 0u; s.far_count = 0; }
                 __syncthreads();
                 SDF_STAT(6)
-                // ---- nearest face of every voxel, bulk-synchronous and balanced:
-                //   (0) bounding boxes of the static face clusters (<= 32 faces each, spatially sorted)
+                // ---- nearest face of every voxel, bulk-synchronous and balanced (work is indexed by voxel):
+                //   (0) per cluster of <= 32 faces (static, spatially sorted): bounding box; per face: its
+                //       bounding box quantised outwards to 1/8 voxel (6 bytes, conservative)
                 //   for each distance band (< 0.5, < 1.25, < 2.5 voxels), nearest first:
-                //   (A) one thread per (voxel, cluster): box distance inside the band and below the
-                //       voxel's best -> (voxel, cluster) pairs; voxels already final are skipped
-                //   (B) one thread per (pair, face of the cluster): face-box distance against R and the
-                //       voxel's best so far -> (voxel, face) candidates
-                //   (C) one thread per candidate: exact point-triangle test, atomicMin into the voxel
+                //     (A) one thread per (voxel, cluster): box distance inside the band and below the voxel's
+                //         best -> (voxel, cluster) pairs; voxels whose best is below the band are final
+                //     (B) one thread per (pair, face of the cluster): quantised face-box distance against R
+                //         and the voxel's best -> (voxel, face) candidates
+                //     (C) one thread per candidate: exact point-triangle test, atomicMin into the voxel
                 //   Processing the bands in order makes (B) reject most faces of the outer bands.
                 for (int c = warp; c < NCL; c += SDF_WARPS) {
                     const ushort4 id = cl_tri[c * 32 + lane];
                     float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+                    uint8_t* fb = s.fbox8 + (c * 32 + lane) * 6;
                     if (id.w) {
                         const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
 #pragma unroll
                         for (int ax = 0; ax < 3; ++ax) {
                             lo[ax] = fminf(A_[ax], fminf(B_[ax], C_[ax]));
                             hi[ax] = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
+                            fb[ax] = (uint8_t)max(0, min(255, (int)floorf((lo[ax] + 1.0f) * 127.5f)));
+                            fb[3 + ax] = (uint8_t)max(0, min(255, (int)ceilf((hi[ax] + 1.0f) * 127.5f)));
                         }
+                    } else {
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) { fb[ax] = 255; fb[3 + ax] = 0; }
                     }
 #pragma unroll
                     for (int ax = 0; ax < 3; ++ax) {
@@ -525,42 +545,36 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                         if (d2 < b_lo || d2 >= b_hi || d2 >= bv) continue;
                         const uint32_t pos = atomicAdd(&s.pn[0], 1u);
                         if (pos < P_CAP) pairs[pos] = ((uint32_t)v << 6) | (uint32_t)c;
-                        else {
-                            // pair queue full (very many marked voxels): this thread handles the cluster itself
-                            for (int l = 0; l < 32; ++l) {
-                                const ushort4 id = cl_tri[c * 32 + l];
-                                if (id.w) pair_test(s, cl_tri, v, c * 32 + l);
-                            }
-                        }
+                        else for (int l = 0; l < 32; ++l) if (cl_tri[c * 32 + l].w) pair_test(s, cl_tri, v, c * 32 + l);
                     }
                     __syncthreads();
-                    // (B) pair x face of the cluster
+                    // (B) pair x face of the cluster, quantised boxes (lower bound of the true box distance)
                     const int np = min((int)s.pn[0], P_CAP);
                     for (int jj = tid; jj < np * 32; jj += SDF_THREADS) {
                         const uint32_t pr = pairs[jj >> 5];
                         const int v = pr >> 6, slot = (pr & 63u) * 32 + (jj & 31);
-                        const ushort4 id = cl_tri[slot];
-                        if (!id.w) continue;
+                        const uint8_t* fb = s.fbox8 + slot * 6;
                         float q[3];
                         voxel_pos(s.worklist[v], q);
-                        const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
                         float d2 = 0.f;
 #pragma unroll
                         for (int ax = 0; ax < 3; ++ax) {
-                            const float lo = fminf(A_[ax], fminf(B_[ax], C_[ax])), hi = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
+                            const float lo = fb[ax] * (1.0f / 127.5f) - 1.0f, hi = fb[3 + ax] * (1.0f / 127.5f) - 1.0f;
                             const float d = fmaxf(fmaxf(lo - q[ax], q[ax] - hi), 0.f);
                             d2 += d * d;
                         }
                         // a face whose box is farther than R or than the voxel's best cannot matter
-                        if (d2 >= SDF_R2 || d2 >= __uint_as_float(s.best[v])) continue;
+                        if (fb[0] > fb[3] || d2 >= SDF_R2 || d2 >= __uint_as_float(s.best[v])) continue;
                         const uint32_t pos = atomicAdd(&s.qn, 1u);
                         if (pos < Q_CAP) s.queue[pos] = ((uint32_t)v << 16) | (uint32_t)slot;
                         else pair_test(s, cl_tri, v, slot);          // queue full: test in place
                     }
                     __syncthreads();
                     // (C) exact tests
-                    const int nq = min((int)s.qn, Q_CAP);
-                    for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) pair_test(s, cl_tri, s.queue[p2] >> 16, s.queue[p2] & 0xffffu);
+                    {
+                        const int nq = min((int)s.qn, Q_CAP);
+                        for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) pair_test(s, cl_tri, s.queue[p2] >> 16, s.queue[p2] & 0xffffu);
+                    }
                     __syncthreads();
                     if (tid == 0) { s.qn = 0u; s.pn[0] = 0u; }
                     __syncthreads();
