@@ -39,14 +39,14 @@ ITERS = 4 * (EPOCHS + 1)
 
 # Algorithmic bytes per launch unit: compulsory op-boundary traffic, fp32.
 ALG_BYTES = {                       # per hand unless noted
-    "pose_prep": 58 * 4 + 152 * 4 + 192 * 4 + 48 * 4,
-    "blend_fwd": 152 * 4 + 2334 * 4,
+    "pose_prep": 58 * 4 + 160 * 4 + 192 * 4 + 48 * 4,
+    "blend_fwd": 160 * 4 + 2334 * 4,
     "skin_fwd": 2334 * 4 + 192 * 4 + 2334 * 4,
     "sdf": 43572 / 2,               # 43,572 B per FRAME
     "frame_loss": (48 * 4 + 15 * 4 + 63 * 4 + 122 * 4) / 1,
     "skin_bwd": 2334 * 4 * 3 + 192 * 4 * 2,
-    "blend_bwd": 2334 * 4 + 152 * 4,
-    "pose_bwd": 192 * 4 + 48 * 4 + 152 * 4 + 58 * 4,
+    "blend_bwd": 2334 * 4 + 160 * 4,
+    "pose_bwd": 192 * 4 + 48 * 4 + 160 * 4 + 58 * 4,
     "step": 61 * 4 * 5,
 }
 STEP_BYTES_PER_FRAME_ITER = 76388   # SURVEY §8(d) op-boundary figure for the fused step

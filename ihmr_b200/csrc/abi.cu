@@ -219,6 +219,18 @@ int ihmr_model_update_shapedirs(ihmr_model_t* m, const float* shapedirs, ihmr_st
     return IHMR_OK;
 }
 
+int ihmr_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                     ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(A && B && C && M >= 0);
+    return launch_gemm_tf32x3(M, Nc, K, A, lda, B, ldb, C, ldc, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_gemm_reference_fp32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                             ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(A && B && C && M >= 0 && K % 8 == 0 && N % 4 == 0);
+    return launch_sgemm_reference(M, N, K, A, lda, B, ldb, C, ldc, static_cast<cudaStream_t>(stream));
+}
+
 size_t ihmr_mano_workspace_bytes(int n_hands) { return n_hands > 0 ? mano_ws_bytes(n_hands) : 0; }
 
 int ihmr_mano_forward(const ihmr_model_t* m, int n, const float* global_orient, const float* hand_pose,

@@ -1,0 +1,206 @@
+// Blend-shape contraction on the 5th-generation tensor cores (tcgen05, accumulators in TMEM).
+//
+//   forward : off (N x 2336) = X (N x 160) . D (160 x 2336)        [posedirs ; shapedirs]
+//   backward: dX  (N x 160)  = gposed (N x 2336) . D^T
+//
+// Both are C[M,Nc] = A[M,K] . B[Nc,K]^T with A and B "K-major" (row-major with K contiguous):
+// forward B = D^T (2336 x 160), backward B = D (160 x 2336).  This is the dense
+// "(B*2) x 135 by 135 x 2334" contraction BASELINE.json's north_star assigns to the tensor
+// cores (smplx lbs: `torch.matmul(pose_feature, posedirs)`, reached from
+// /root/reference/src/models/optimize_model.py:194), with the shape blend folded in.
+//
+// fp32 accuracy on a TF32 pipe: every operand is split in registers on its way to shared
+// memory, x = hi + lo with hi = x rounded down to 10 mantissa bits (exact in TF32) and
+// lo = x - hi (exact in fp32), and three MMAs are issued per K step: hi*hi + lo*hi + hi*lo.
+// The dropped lo*lo term is ~2^-22 relative; accumulation is fp32 in TMEM.
+//
+// One CTA (4 warps) computes a 128 x BN tile: K is consumed in chunks of 32 (all threads load
+// and split the chunk into the canonical no-swizzle K-major core-matrix layout, one elected
+// thread issues 4 K-steps x 3 MMAs and commits to an mbarrier), then each warp drains its 32
+// TMEM lanes with tcgen05.ld and writes its rows.  Two CTAs per SM overlap one CTA's loads with
+// the other's MMAs.
+#include "kernels.cuh"
+
+namespace ihmr {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // K elements per chunk = 8 core-matrix columns of 16 bytes
+constexpr int TC_THREADS = 128;
+constexpr uint32_t TC_LBO = 128;          // bytes between core matrices adjacent in K
+constexpr uint32_t TC_SBO = 1024;         // bytes between 8-row groups: 8 K-columns x 128 bytes
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): 8 x 16-byte core matrices
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);            // start address, 16-byte units
+    d |= (uint64_t)((TC_LBO >> 4) & 0x3fffu) << 16;     // leading byte offset
+    d |= (uint64_t)((TC_SBO >> 4) & 0x3fffu) << 32;     // stride byte offset
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    return d;                                           // base offset 0, layout type 0 = no swizzle
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// float4 of row-major src -> (hi, lo) 16-byte core-matrix rows
+__device__ __forceinline__ void split_store(float4 v, float4* hi_dst, float4* lo_dst) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    *hi_dst = h;
+    *lo_dst = l;
+}
+
+// rows x 32 chunk of a K-major matrix -> canonical layout [row/8][kcol 0..7][row%8][16 B], split hi/lo.
+// Lane mapping: 8 consecutive rows x 4 consecutive K-columns per warp access = 512 contiguous bytes.
+__device__ __forceinline__ void load_chunk(const float* __restrict__ src, int ld, int row0, int rows_valid, int rows_tile,
+                                           int k0, unsigned char* hi, unsigned char* lo, int tid) {
+    const int items = rows_tile * 8;                       // (row, kcol) pairs
+    for (int it = tid; it < items; it += TC_THREADS) {
+        const int r8 = it & 7, kc_lo = (it >> 3) & 3, blk = it >> 5;      // blk enumerates (row group, kcol high bit)
+        const int kc = kc_lo + 4 * (blk & 1), rg = blk >> 1;
+        const int r = rg * 8 + r8;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_valid) v = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k0 + kc * 4);
+        const uint32_t off = rg * TC_SBO + kc * TC_LBO + r8 * 16;
+        split_store(v, reinterpret_cast<float4*>(hi + off), reinterpret_cast<float4*>(lo + off));
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS)
+k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+              float* __restrict__ C, int ldc) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = a_hi + TC_BM * TC_BK * 4;
+    unsigned char* b_hi = a_lo + TC_BM * TC_BK * 4;
+    unsigned char* b_lo = b_hi + BN * TC_BK * 4;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    const int rows_a = min(TC_BM, M - m0);
+    const int rows_b = min(BN, Nc - n0);
+    const int n_inst = (rows_b + 15) & ~15;               // MMA N: multiple of 16 covering the valid B rows
+    constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = umma_idesc(n_inst);
+
+    uint32_t parity = 0;
+    const int nchunks = K / TC_BK;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        load_chunk(A, lda, m0, rows_a, TC_BM, ch * TC_BK, a_hi, a_lo, tid);
+        load_chunk(B, ldb, n0, rows_b, n_inst, ch * TC_BK, b_hi, b_lo, tid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (tensor core)
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                const uint32_t koff = ks * 2 * TC_LBO;               // 8 tf32 = two 16-byte core-matrix columns
+                const uint64_t ah = umma_desc(smem_u32(a_hi) + koff), al = umma_desc(smem_u32(a_lo) + koff);
+                const uint64_t bh = umma_desc(smem_u32(b_hi) + koff), bl = umma_desc(smem_u32(b_lo) + koff);
+                umma_tf32(tmem_d, ah, bh, idesc, ch > 0 || ks > 0);
+                umma_tf32(tmem_d, al, bh, idesc, true);
+                umma_tf32(tmem_d, ah, bl, idesc, true);
+            }
+            // arrives on the mbarrier when all MMAs issued so far have completed (implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+        }
+        mbar_wait(smem_u32(&mbar), parity);                          // operands may be overwritten, accumulator is current
+        parity ^= 1;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows m0 + 32w + lane
+    const int row = m0 + warp * 32 + lane;
+    for (int c0 = 0; c0 < n_inst; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+            float* dst = C + (size_t)row * ldc + n0 + c0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (n0 + c0 + q * 4 < Nc)
+                    *reinterpret_cast<float4*>(dst + q * 4) =
+                        make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(TMEM_COLS) : "memory");
+}
+
+template <int BN>
+static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * TC_BM + 2 * BN) * TC_BK * 4;
+    static bool configured = false;
+    if (!configured) {
+        IHMR_CUDA_OK(cudaFuncSetAttribute(k_gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((Nc + BN - 1) / BN, (M + TC_BM - 1) / TC_BM);
+    k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, C, ldc);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+// C[M,Nc] = A[M,K] . B[Nc,K]^T ; K % 32 == 0, Nc % 4 == 0, lda/ldb/ldc % 4 == 0
+int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       cudaStream_t st) {
+    if (M <= 0) return IHMR_OK;
+    if (K % TC_BK || Nc % 4 || lda % 4 || ldb % 4 || ldc % 4) { set_error("gemm_tf32x3: unsupported shape"); return IHMR_E_INVALID; }
+    if (Nc > 160) return launch_tc<256>(M, Nc, K, A, lda, B, ldb, C, ldc, st);
+    return launch_tc<160>(M, Nc, K, A, lda, B, ldb, C, ldc, st);
+}
+
+}  // namespace ihmr

@@ -15,7 +15,7 @@ constexpr int NB = IHMR_NUM_BETAS;        // 10
 constexpr int NPF = IHMR_NUM_POSE_FEAT;   // 135
 constexpr int NC = NV * 3;                // 2334 blend-shape columns
 constexpr int LDN = 2336;                 // padded column count / row stride of (hands x 2334) buffers
-constexpr int KP = 152;                   // blend rows: 135 pose features + 10 betas + 7 zero pad
+constexpr int KP = 160;                   // blend rows: 135 pose features + 10 betas + 15 zero pad (5 chunks of 32)
 constexpr int PD = IHMR_PARAM_DIM;        // 122
 
 // offsets inside a (B,122) parameter row

@@ -44,6 +44,12 @@ int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
                     const float* gtips, float* gposed, float* dA, cudaStream_t st);
 int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st);
+// C[M,Nc] = A[M,K] . B[Nc,K]^T on tcgen05 with 3xTF32 splitting (blend_tc.cu)
+int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       cudaStream_t st);
+// C[M,N] = A[M,K] . B[K,N] on the FP32 pipe: reference for the tensor-core path (tests only)
+int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                           cudaStream_t st);
 int launch_pose_bwd(const ihmr_model* m, int n, HandSrc src, const float* dA, const float* gjoints,
                     const float* dX, HandGrad out, cudaStream_t st);
 

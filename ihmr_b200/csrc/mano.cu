@@ -625,17 +625,20 @@ int launch_pose_prep(const ihmr_model* m, int n, HandSrc src, float* X, float* A
 }
 
 int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cudaStream_t st) {
-    if (n <= 0) return IHMR_OK;
-    dim3 grid((LDN + 127) / 128, (n + 127) / 128);
-    k_sgemm<128, 128, 8, 8, 8><<<grid, 256, 0, st>>>(n, LDN, KP, X, KP, m->D, LDN, off, LDN);
-    IHMR_LAUNCH_OK();
-    return IHMR_OK;
+    // off (n x 2336) = X (n x 160) . D  ==  X . (D^T)^T  with D^T (2336 x 160) K-major
+    return launch_gemm_tf32x3(n, LDN, KP, X, KP, m->DT, KP, off, LDN, st);
 }
 
 int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st) {
-    if (n <= 0) return IHMR_OK;
-    dim3 grid(1, (n + 63) / 64);
-    k_sgemm<64, 160, 8, 8, 5><<<grid, 256, 0, st>>>(n, KP, LDN, gposed, LDN, m->DT, KP, dX, KP);
+    // dX (n x 160) = gposed (n x 2336) . D^T  with D (160 x 2336) K-major
+    return launch_gemm_tf32x3(n, KP, LDN, gposed, LDN, m->D, LDN, dX, KP, st);
+}
+
+int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                           cudaStream_t st) {
+    if (M <= 0) return IHMR_OK;
+    dim3 grid((N + 127) / 128, (M + 127) / 128);
+    k_sgemm<128, 128, 8, 8, 8><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }

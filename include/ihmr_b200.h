@@ -81,6 +81,16 @@ int ihmr_mano_backward(const ihmr_model_t* model, int n_hands, const float* glob
                        float* grad_betas, void* workspace, size_t workspace_bytes,
                        ihmr_stream_t stream);
 
+/* The blend-shape contraction of the MANO layer (`torch.matmul(pose_feature, posedirs)` plus the
+ * shape blend in smplx lbs) exposed on its own, for tests and measurements:
+ * ihmr_gemm_tf32x3: C[M,Nc] = A[M,K] . B[Nc,K]^T on the tcgen05 tensor cores with 3xTF32 splitting
+ * (K % 32 == 0, Nc/lda/ldb/ldc % 4 == 0); ihmr_gemm_reference_fp32: C[M,N] = A[M,K] . B[K,N] on the
+ * FP32 pipe, the checker the tensor-core path is tested against (not used by the product path). */
+int ihmr_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                     ihmr_stream_t stream);
+int ihmr_gemm_reference_fp32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                             int ldc, ihmr_stream_t stream);
+
 /* ---- interpenetration loss (a10) ------------------------------------------------------
  * Replaces `SDFLoss(faces_right, faces_left, robustifier)(hand_verts, return_per_vert_loss=True,
  * return_origin_scale_loss=True)` at src/models/loss_utils.py:181-182 including the `sdf_cuda`
