@@ -76,18 +76,46 @@ __device__ __forceinline__ void split_store(float4 v, float4* hi_dst, float4* lo
 }
 
 // rows x 32 chunk of a K-major matrix -> canonical layout [row/8][kcol 0..7][row%8][16 B], split hi/lo.
-// Lane mapping: 8 consecutive rows x 4 consecutive K-columns per warp access = 512 contiguous bytes.
-__device__ __forceinline__ void load_chunk(const float* __restrict__ src, int ld, int row0, int rows_valid, int rows_tile,
-                                           int k0, unsigned char* hi, unsigned char* lo, int tid) {
-    const int items = rows_tile * 8;                       // (row, kcol) pairs
-    for (int it = tid; it < items; it += TC_THREADS) {
-        const int r8 = it & 7, kc_lo = (it >> 3) & 3, blk = it >> 5;      // blk enumerates (row group, kcol high bit)
-        const int kc = kc_lo + 4 * (blk & 1), rg = blk >> 1;
-        const int r = rg * 8 + r8;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < rows_valid) v = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k0 + kc * 4);
-        const uint32_t off = rg * TC_SBO + kc * TC_LBO + r8 * 16;
-        split_store(v, reinterpret_cast<float4*>(hi + off), reinterpret_cast<float4*>(lo + off));
+// Lane mapping: 8 consecutive rows x 4 consecutive K-columns per warp access = 512 contiguous bytes of
+// shared memory.  The chunk is fetched into registers first (all loads in flight together, and in flight
+// while the previous chunk's MMAs run) and split + stored afterwards.
+template <int NITEMS>
+struct ChunkRegs {
+    float4 v[NITEMS];
+};
+
+__device__ __forceinline__ void item_coords(int it, int& r, int& kc, uint32_t& off) {
+    const int r8 = it & 7, kc_lo = (it >> 3) & 3, blk = it >> 5;      // blk enumerates (row group, kcol high bit)
+    kc = kc_lo + 4 * (blk & 1);
+    const int rg = blk >> 1;
+    r = rg * 8 + r8;
+    off = rg * TC_SBO + kc * TC_LBO + r8 * 16;
+}
+
+template <int NITEMS>
+__device__ __forceinline__ void fetch_chunk(ChunkRegs<NITEMS>& regs, const float* __restrict__ src, int ld, int row0,
+                                            int rows_valid, int rows_tile, int k0, int tid) {
+#pragma unroll
+    for (int i = 0; i < NITEMS; ++i) {
+        const int it = tid + i * TC_THREADS;
+        int r, kc;
+        uint32_t off;
+        item_coords(it, r, kc, off);
+        regs.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it < rows_tile * 8 && r < rows_valid)
+            regs.v[i] = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + k0 + kc * 4);
+    }
+}
+
+template <int NITEMS>
+__device__ __forceinline__ void store_chunk(const ChunkRegs<NITEMS>& regs, int rows_tile, unsigned char* hi, unsigned char* lo, int tid) {
+#pragma unroll
+    for (int i = 0; i < NITEMS; ++i) {
+        const int it = tid + i * TC_THREADS;
+        int r, kc;
+        uint32_t off;
+        item_coords(it, r, kc, off);
+        if (it < rows_tile * 8) split_store(regs.v[i], reinterpret_cast<float4*>(hi + off), reinterpret_cast<float4*>(lo + off));
     }
 }
 
@@ -125,9 +153,13 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
 
     uint32_t parity = 0;
     const int nchunks = K / TC_BK;
+    ChunkRegs<TC_BM * 8 / TC_THREADS> ra;
+    ChunkRegs<BN * 8 / TC_THREADS> rb;
+    fetch_chunk(ra, A, lda, m0, rows_a, TC_BM, 0, tid);
+    fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, 0, tid);
     for (int ch = 0; ch < nchunks; ++ch) {
-        load_chunk(A, lda, m0, rows_a, TC_BM, ch * TC_BK, a_hi, a_lo, tid);
-        load_chunk(B, ldb, n0, rows_b, n_inst, ch * TC_BK, b_hi, b_lo, tid);
+        store_chunk(ra, TC_BM, a_hi, a_lo, tid);
+        store_chunk(rb, n_inst, b_hi, b_lo, tid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (tensor core)
         __syncthreads();
         if (tid == 0) {
@@ -144,13 +176,19 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
             // arrives on the mbarrier when all MMAs issued so far have completed (implies fence::before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
         }
+        if (ch + 1 < nchunks) {                                      // next chunk's global loads fly while the MMAs run
+            fetch_chunk(ra, A, lda, m0, rows_a, TC_BM, (ch + 1) * TC_BK, tid);
+            fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, (ch + 1) * TC_BK, tid);
+        }
         mbar_wait(smem_u32(&mbar), parity);                          // operands may be overwritten, accumulator is current
         parity ^= 1;
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows m0 + 32w + lane
-    const int row = m0 + warp * 32 + lane;
+    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows m0 + 32w + lane.  tcgen05.ld hands every lane
+    // 32 consecutive columns of ITS row; the 32 x 32 block goes through shared memory (the operand buffers
+    // are free now) so that each store instruction of the warp writes four complete 128-byte row segments.
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
     for (int c0 = 0; c0 < n_inst; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
@@ -164,15 +202,20 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < M) {
-            float* dst = C + (size_t)row * ldc + n0 + c0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (n0 + c0 + q * 4 < Nc)
-                    *reinterpret_cast<float4*>(dst + q * 4) =
-                        make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-            }
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stage + lane * 36 + q * 4) =
+                make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+        __syncwarp();
+        const int cq = (lane & 7) * 4;                       // this lane's 4 columns inside the 32-column block
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = (lane >> 3) + 4 * i;               // row inside the warp's 32 rows
+            const int row = m0 + warp * 32 + r;
+            if (row < M && n0 + c0 + cq < Nc)
+                *reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + c0 + cq) = *reinterpret_cast<const float4*>(stage + r * 36 + cq);
         }
+        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
