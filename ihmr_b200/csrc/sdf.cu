@@ -331,6 +331,12 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             thi[c] = (s.box[h][1][c] - cen[c]) / scale + 1e-4f;
         }
 
+        float wlo[3], whi[3];                // the same box in world units, grown by one voxel (+ slack)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            wlo[c] = s.box[h][0][c] - scale * (2.2f / G);
+            whi[c] = s.box[h][1][c] + scale * (2.2f / G);
+        }
         for (int i = tid; i < G * G; i += SDF_THREADS) { s.needed[i] = 0u; s.work[i] = 0u; }
         if (tid < G) s.row_mask[tid] = 0u;
         __syncthreads();
@@ -350,7 +356,10 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             if (v < NV) {
                 float p[3];
                 load_vert(o, v, p);
-                bool in = true;
+                // only vertices within one voxel of the grid hand's own box can touch a voxel that may be inside
+                // (no lower limit in x: behind the open wrist, voxels left of the mesh can have odd parity)
+                bool in = p[0] <= whi[0] && p[1] >= wlo[1] && p[1] <= whi[1] && p[2] >= wlo[2] && p[2] <= whi[2];
+                if (!in) continue;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float pn = (p[c] - cen[c]) / scale;
