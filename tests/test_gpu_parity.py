@@ -248,3 +248,70 @@ def test_determinism_and_shard_invariance(model_root, oracle_layers):
     for k in ("pred_pose_params", "pred_shape_params", "pred_hand_trans", "pred_joints_3d", "collision_loss"):
         assert np.array_equal(full1[k], full2[k]), k                       # run-to-run bitwise
         assert np.array_equal(np.concatenate([h[k] for h in halves]), full1[k]), k   # sharding bitwise
+
+
+# ------------------------------------------------- less-travelled options of the reference
+def test_sgd_optimizer_matches_oracle_loop(model_root, oracle_layers):
+    """opt.optimizer == 'sgd' (optimize_model.py:345-347): SGD with momentum 0.9."""
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default, with_epochs
+    from oracle import host_loop_oracle as HL
+    from oracle import sdf_oracle
+    B, epochs, freq = 2, 3, 1
+    batch = H.torch_batch(H.make_batch(oracle_layers[0], 2, B))
+    sdf = sdf_oracle.SDFLoss(oracle_layers[0].faces, oracle_layers[1].faces)
+    cpu = HL.HostLoopOracle(oracle_layers[0], oracle_layers[0].faces, oracle_layers[1].faces, sdf, B,
+                            strategy=HL.opt_default_strategy(epochs), save_mid_freq=freq, optimizer="sgd")
+    cpu.set_input(batch); cpu.init_optimize(); cpu.optimize()
+    ref = cpu.get_pred_result()
+    opt = H.make_opt(model_root, B, save_mid_freq=freq, strategy=with_epochs(opt_default, epochs))
+    opt.optimizer = "sgd"
+    m = OptimizeModel(opt)
+    m.set_input(batch); m.init_optimize(); m.optimize(0, 1)
+    res = m.get_pred_result()
+    assert np.abs(res["pred_joints_3d"] - ref["pred_joints_3d"]).max() <= JOINT_TOL
+    assert np.abs(res["pred_pose_params"] - ref["pred_pose_params"]).max() <= 1e-4
+
+
+def test_sdf_robustifier_matches_oracle(cuda_layers, oracle_layers):
+    """robustifier > 0 is the training-time setting (loss_utils.py:36); rho(x) = (x/r)^2 / ((x/r)^2 + 1)."""
+    from ihmr_b200 import sdf_loss, synthetic
+    from oracle import mano_oracle, sdf_oracle
+    raw = synthetic.make_raw_frames(0, 3, seed=0, mode="collision")
+    with torch.no_grad():
+        rv, lv, _ = mano_oracle.two_hand_forward(oracle_layers[0], torch.tensor(raw["true_pose"]),
+                                                 torch.tensor(raw["true_shape"]), torch.tensor(raw["true_trans"]))
+    hv_cpu = torch.stack([rv, lv], 1).clone().requires_grad_(True)
+    l_ref, pv_ref, o_ref = sdf_oracle.SDFLoss(oracle_layers[0].faces, oracle_layers[1].faces, robustifier=0.05)(hv_cpu, True, True)
+    l_ref.sum().backward()
+    hv = hv_cpu.detach().cuda().requires_grad_(True)
+    l, pv, o = sdf_loss.SDFLoss(cuda_layers[0].faces, cuda_layers[1].faces, robustifier=0.05).cuda()(
+        hv, return_per_vert_loss=True, return_origin_scale_loss=True)
+    l.sum().backward()
+    assert rel_err(l.detach().cpu().numpy(), l_ref.detach().numpy()) <= REL_TOL
+    assert float((pv.cpu() - pv_ref.detach()).abs().max()) <= 1e-4 * float(pv_ref.max())
+    assert float((o.cpu() - o_ref).abs().max()) <= 2e-6
+    assert rel_err(hv.grad.cpu().numpy(), hv_cpu.grad.numpy()) <= REL_TOL
+
+
+def test_camera_gradient_and_stage(model_root, oracle_layers):
+    """The commented-out camera stage of opt_default.py:81-97 is still expressible: 'pred_cam_params'
+    as update target. Its gradient flows through the 2-D term only."""
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default
+    B = 2
+    batch = H.torch_batch(H.make_batch(oracle_layers[0], 0, B))
+    stage = dict(opt_default[1], update_params=["pred_cam_params"], filter_loss=[("joints_2d_loss_p", "+0")],
+                 select_loss="joints_2d_loss_p", epoch=5, lr=1e-2)
+    hl = H.oracle_loop(oracle_layers, B, 1, 1)
+    hl.set_input(batch); hl.init_optimize()
+    hl.pred_cam_params = hl.pred_cam_params.clone().requires_grad_(True)
+    hl.forward(); hl.compute_loss(stage["loss_weights"]); hl.loss.backward()
+    m = OptimizeModel(H.make_opt(model_root, B, save_mid_freq=1))
+    m.set_input(batch); m.init_optimize()
+    _, grad = m.value_and_grad(stage)
+    assert rel_err(grad[:, 0:3].cpu().numpy(), hl.pred_cam_params.grad.numpy()) <= REL_TOL
+    before = m.value_and_grad(stage)[0][0].item()
+    m.run_stage(stage)
+    after = m.value_and_grad(stage)[0][0].item()
+    assert after <= before * 1.001                        # selection never accepts a worse 2-D loss
