@@ -15,7 +15,7 @@ EXPORTS = (
     "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",
     "ihmr_model_update_shapedirs", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
     "ihmr_mano_backward", "ihmr_sdf_loss", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
-    "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32",
+    "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics",
 )
 KERNEL_CLASSES = ("pose_prep", "blend_fwd", "skin_fwd", "sdf", "frame_loss", "skin_bwd", "blend_bwd", "pose_bwd", "step")
 
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     for fn in (lib.ihmr_gemm_tf32x3, lib.ihmr_gemm_reference_fp32):
         fn.restype = i32
         fn.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
+    lib.ihmr_eval_metrics.restype = i32
+    lib.ihmr_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     lib.ihmr_sdf_stats.restype = i32
     lib.ihmr_sdf_stats.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.ihmr_launch_count.restype = C.c_ulonglong

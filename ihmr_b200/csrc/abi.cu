@@ -290,6 +290,12 @@ int ihmr_sdf_stats(const ihmr_model_t* m, int n_frames, const float* hand_verts,
     return launch_sdf(m, n_frames, a, static_cast<cudaStream_t>(stream));
 }
 
+int ihmr_eval_metrics(int n_frames, const float* pred_joints_3d, const float* gt_joints_3d, const float* collision_origin_scale,
+                      const float* scale, float* out, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(n_frames >= 0 && pred_joints_3d && gt_joints_3d && collision_origin_scale && out);
+    return launch_eval_metrics(n_frames, pred_joints_3d, gt_joints_3d, collision_origin_scale, scale, out, static_cast<cudaStream_t>(stream));
+}
+
 size_t ihmr_opt_workspace_bytes(int n_frames) { return n_frames > 0 ? opt_ws_bytes(n_frames) : 0; }
 
 static int check_targets(const ihmr_targets_t* t) {

@@ -76,4 +76,8 @@ struct SdfArgs {
 };
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
 
+// per-frame evaluator metrics (eval.cu): out (B,6)
+int launch_eval_metrics(int B, const float* pred, const float* gt, const float* origin, const float* scale, float* out,
+                        cudaStream_t st);
+
 }  // namespace ihmr

@@ -164,6 +164,18 @@ int ihmr_opt_value_and_grad(const ihmr_model_t* model, int n_frames, int bs_norm
                             float* grad, void* workspace, size_t workspace_bytes,
                             ihmr_stream_t stream);
 
+/* ---- evaluator metrics on the device ------------------------------
+ * Replaces the host-side per-frame metric code the reference runs after get_pred_result:
+ * mu.get_single_joints_error and mu.get_single_pa_inter_joints_error(use_rot=False)
+ * (src/utils/metric_utils.py:23-38,107-143, called at src/utils/evaluator.py:74-86) and the
+ * collision mean / max of src/utils/evaluator.py:163-181.  pred_joints_3d (n,42,3), gt_joints_3d
+ * (n,42,4: xyz + validity), collision_origin_scale (n,1556), scale (n) or NULL (= 1) ->
+ * out (n,6) = [sum of joint errors, count, sum of no-rotation Procrustes errors, count,
+ * mean collision, max collision] in the units of the inputs (metres). */
+int ihmr_eval_metrics(int n_frames, const float* pred_joints_3d, const float* gt_joints_3d,
+                      const float* collision_origin_scale, const float* scale, float* out,
+                      ihmr_stream_t stream);
+
 /* Measurement aid (the one entry point that synchronises `stream`): runs ONE iteration of the
  * stage (forward, losses, backward, a zero-length optimiser step) with a CUDA event after each
  * kernel class and returns the 9 device times in milliseconds:
