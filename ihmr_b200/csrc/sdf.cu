@@ -33,7 +33,16 @@ constexpr int PHI_CAP = 4096;       // voxels evaluated per pass (more voxels: f
 constexpr int Q_CAP = 2048;         // queued candidates (overflow is processed in place)
 constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
 constexpr int P_CAP = 2048;         // queued (voxel, cluster) pairs of one distance band
-constexpr float SDF_R = 2.5f * (2.0f / G);   // candidate radius of the face-centric pass (2.5 voxels)
+#ifndef SDF_R_CELLS
+#define SDF_R_CELLS 2.5f
+#endif
+#ifndef SDF_BAND0
+#define SDF_BAND0 0.35f
+#endif
+#ifndef SDF_BAND1
+#define SDF_BAND1 1.0f
+#endif
+constexpr float SDF_R = SDF_R_CELLS * (2.0f / G);   // candidate radius of the banded search, in voxels
 constexpr float SDF_R2 = SDF_R * SDF_R;
 
 struct __align__(16) SdfSmem {
@@ -491,7 +500,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 // ---- nearest face of every voxel, bulk-synchronous and balanced (work is indexed by voxel):
                 //   (0) per cluster of <= 32 faces (static, spatially sorted): bounding box; per face: its
                 //       bounding box quantised outwards to 1/8 voxel (6 bytes, conservative)
-                //   for each distance band (< 0.5, < 1.25, < 2.5 voxels), nearest first:
+                //   for each distance band (< 0.35, < 1.0, < 2.5 voxels; measured best of five settings), nearest first:
                 //     (A) one thread per (voxel, cluster): box distance inside the band and below the voxel's
                 //         best -> (voxel, cluster) pairs; voxels whose best is below the band are final
                 //     (B) one thread per (pair, face of the cluster): quantised face-box distance against R
@@ -533,7 +542,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 uint32_t* pairs = reinterpret_cast<uint32_t*>(s.far_list);      // far_list is free until the classification
                 static_assert(sizeof(s.far_list) >= P_CAP * sizeof(uint32_t), "pair queue aliases far_list");
                 constexpr float cell = 2.0f / G;
-                const float band_hi[3] = {(0.5f * cell) * (0.5f * cell), (1.25f * cell) * (1.25f * cell), SDF_R2};
+                const float band_hi[3] = {(SDF_BAND0 * cell) * (SDF_BAND0 * cell), (SDF_BAND1 * cell) * (SDF_BAND1 * cell), SDF_R2};
                 for (int band = 0; band < 3; ++band) {
                     const float b_lo = band ? band_hi[band - 1] : 0.f, b_hi = band_hi[band];
                     // (A) voxel x cluster.  A voxel whose best is below the previous band limit is final:
