@@ -14,7 +14,7 @@
 // lo = x - hi (exact in fp32), and three MMAs are issued per K step: hi*hi + lo*hi + hi*lo.
 // The dropped lo*lo term is ~2^-22 relative; accumulation is fp32 in TMEM.
 //
-// One CTA (4 warps) computes a 128 x BN tile: K is consumed in chunks of 32 (all threads load
+// One CTA (8 warps) computes a 128 x BN tile: K is consumed in chunks of 32 (all threads load
 // and split the chunk into the canonical no-swizzle K-major core-matrix layout, one elected
 // thread issues 4 K-steps x 3 MMAs and commits to an mbarrier), then each warp drains its 32
 // TMEM lanes with tcgen05.ld and writes its rows.  Two CTAs per SM overlap one CTA's loads with
@@ -25,7 +25,7 @@ namespace ihmr {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // K elements per chunk = 8 core-matrix columns of 16 bytes
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;            // 8 warps: all load; warp w drains TMEM lane quarter w % 4, column half w / 4
 constexpr uint32_t TC_LBO = 128;          // bytes between core matrices adjacent in K
 constexpr uint32_t TC_SBO = 1024;         // bytes between 8-row groups: 8 K-columns x 128 bytes
 
@@ -189,9 +189,10 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
     // 32 consecutive columns of ITS row; the 32 x 32 block goes through shared memory (the operand buffers
     // are free now) so that each store instruction of the warp writes four complete 128-byte row segments.
     float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
-    for (int c0 = 0; c0 < n_inst; c0 += 32) {
+    const int quarter = warp & 3;                          // a warp can only read TMEM lanes 32 (w % 4) .. +31
+    for (int c0 = (warp >> 2) * 32; c0 < n_inst; c0 += 64) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -210,8 +211,8 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
         const int cq = (lane & 7) * 4;                       // this lane's 4 columns inside the 32-column block
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int r = (lane >> 3) + 4 * i;               // row inside the warp's 32 rows
-            const int row = m0 + warp * 32 + r;
+            const int r = (lane >> 3) + 4 * i;               // row inside the quarter's 32 rows
+            const int row = m0 + quarter * 32 + r;
             if (row < M && n0 + c0 + cq < Nc)
                 *reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + c0 + cq) = *reinterpret_cast<const float4*>(stage + r * 36 + cq);
         }

@@ -397,7 +397,7 @@ constexpr int SK_THREADS = 416;   // 13 warps x 2 vertex slots = 832 >= 778
 constexpr int SK_SLOTS = 2;
 constexpr int SK_HPC = 8;         // hands per CTA
 
-__global__ void __launch_bounds__(SK_THREADS)
+__global__ void __launch_bounds__(SK_THREADS, 2)
 k_skin_fwd(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
            const float* __restrict__ Wt, float* __restrict__ verts) {
     __shared__ float4 sA[SK_HPC][48];
