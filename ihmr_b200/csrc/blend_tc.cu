@@ -227,11 +227,8 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
 template <int BN>
 static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st) {
     const size_t smem = (size_t)(2 * TC_BM + 2 * BN) * TC_BK * 4;
-    static bool configured = false;
-    if (!configured) {
-        IHMR_CUDA_OK(cudaFuncSetAttribute(k_gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static unsigned long long configured = 0ull;
+    if (int rc = ensure_dynamic_smem(k_gemm_tf32x3<BN>, smem, configured)) return rc;
     dim3 grid((Nc + BN - 1) / BN, (M + TC_BM - 1) / TC_BM);
     k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, C, ldc);
     IHMR_LAUNCH_OK();

@@ -25,6 +25,21 @@ constexpr int P_R_ORIENT = 6, P_R_POSE = 9, P_L_ORIENT = 54, P_L_POSE = 57, P_R_
 void set_error(const char* fmt, ...);
 void count_launch();   // every kernel launch of this library passes through IHMR_LAUNCH_OK
 
+// cudaFuncSetAttribute is per device: opt a kernel in to a large dynamic shared-memory size once per
+// (kernel, device).  `done` is a per-kernel bitmask of devices; a race only repeats the same call.
+template <typename K>
+inline int ensure_dynamic_smem(K kernel, size_t bytes, unsigned long long& done) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return IHMR_E_CUDA; }
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return IHMR_E_CUDA; }
+        done |= bit;
+    }
+    return IHMR_OK;
+}
+
 #define IHMR_CUDA_OK(expr)                                                              \
     do {                                                                                \
         cudaError_t e__ = (expr);                                                       \

@@ -491,11 +491,32 @@ k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, co
     const int h0 = blockIdx.x * SK_HPC;
     const int nh = min(SK_HPC, n - h0);
 
-    const float4* W4g = reinterpret_cast<const float4*>(W4);
-    for (int i = tid; i < 4 * NV; i += SKB_THREADS) sW4[i] = W4g[i];
-    const float4* A4 = reinterpret_cast<const float4*>(A) + (size_t)h0 * 48;
-    for (int i = tid; i < nh * 48; i += SKB_THREADS) sA[i] = A4[i];
-    __syncthreads();
+    // Stage the skinning weights (49.8 KB, tile-major) and this CTA's joint transforms with the TMA engine:
+    // two 1-D bulk copies global -> shared that complete on an mbarrier, issued by one thread while the
+    // others go straight to waiting (no register round trip, no per-thread address arithmetic).
+    __shared__ __align__(8) uint64_t tma_bar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+    constexpr uint32_t W4_BYTES = 4 * NV * 16;
+    const uint32_t a_bytes = (uint32_t)nh * 48 * 16;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(W4_BYTES + a_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(sW4)), "l"(W4), "r"(W4_BYTES), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(sA)), "l"(A + (size_t)h0 * 192), "r"(a_bytes), "r"(bar) : "memory");
+    }
+    __syncthreads();                                   // the barrier word is initialised before anyone polls it
+    {
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        } while (!done);
+    }
 
     for (int hh = 0; hh < nh; ++hh) {
         const size_t h = h0 + hh;
@@ -653,11 +674,8 @@ int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
                     const float* gtips, float* gposed, float* dA, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
-    static bool configured = false;   // idempotent attribute; a race only repeats the same call
-    if (!configured) {
-        IHMR_CUDA_OK(cudaFuncSetAttribute(k_skin_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_BWD_SMEM));
-        configured = true;
-    }
+    static unsigned long long configured = 0ull;
+    if (int rc = ensure_dynamic_smem(k_skin_bwd, SKIN_BWD_SMEM, configured)) return rc;
     k_skin_bwd<<<(n + SK_HPC - 1) / SK_HPC, SKB_THREADS, SKIN_BWD_SMEM, st>>>(n, off, A, m->vtemp, m->W4,
                                                                            gverts, gtips, gposed, dA);
     IHMR_LAUNCH_OK();
