@@ -44,6 +44,11 @@ int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
                     const float* gtips, float* gposed, float* dA, cudaStream_t st);
 int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st);
+// orientation-only stages (fused layout only): cache L = R0^T (x - J0), then x = R0 L + J0 and its backward
+int launch_rigid_prep(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
+int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
+int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips, const float* gjoints, const float* Lv,
+                     const float* Lj, float* params_grad, cudaStream_t st);
 // C[M,Nc] = A[M,K] . B[Nc,K]^T on tcgen05 with 3xTF32 splitting (blend_tc.cu)
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                        cudaStream_t st);

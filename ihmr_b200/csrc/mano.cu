@@ -604,6 +604,131 @@ k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, co
 
 constexpr size_t SKIN_BWD_SMEM = sizeof(float4) * (4 * NV + 2 * NV + SK_HPC * 48) + sizeof(float) * SKB_KSLICES * 192;
 
+// ------------------------------------------------------------------ rigid (orientation-only) path
+// When a stage updates nothing but the two global orientations (opt_default stage 1,
+// /root/reference/src/strategies/opt_default.py:23-40) every vertex and joint of a hand is an affine
+// function of its root rotation:  x = R0 L + J0  with  L = R0_init^T (x_init - J0)  fixed for the stage
+// (G_j = G_0 H_j with H_j independent of the root rotation; the wrist J0 does not depend on it either).
+// The stage's first iteration runs the generic layer and k_rigid_prep caches L; afterwards the forward
+// is one 3x3 transform per point and the backward one 3x3 reduction per hand.
+template <bool FUSED>
+__device__ __forceinline__ void root_rotation(const HandSrc& src, int h, float* r, float& theta, float* R) {
+    if (FUSED) {
+        const float* row = src.params + (size_t)(h >> 1) * PD + P_POSE + 48 * (h & 1);
+        r[0] = row[0]; r[1] = row[1]; r[2] = row[2];
+        if (h & 1) { r[1] = -r[1]; r[2] = -r[2]; }
+    } else {
+        r[0] = src.orient[(size_t)h * 3]; r[1] = src.orient[(size_t)h * 3 + 1]; r[2] = src.orient[(size_t)h * 3 + 2];
+    }
+    rodrigues(r, theta, R);
+}
+
+constexpr int RG_THREADS = 256;
+
+// mode 0: L = R0^T (x - J0) from the generic forward's verts/joints; mode 1: x = R0 L + J0
+template <int MODE>
+__global__ void __launch_bounds__(RG_THREADS)
+k_rigid_xform(int n, HandSrc src, float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ Lv,
+              float* __restrict__ Lj) {
+    const int h = blockIdx.x, tid = threadIdx.x;
+    float r[3], theta, R[9];
+    root_rotation<true>(src, h, r, theta, R);
+    const float J0[3] = {joints[(size_t)h * 48], joints[(size_t)h * 48 + 1], joints[(size_t)h * 48 + 2]};
+    for (int i = tid; i < NV + NJ; i += RG_THREADS) {
+        float* x = i < NV ? verts + ((size_t)h * NV + i) * 3 : joints + ((size_t)h * NJ + (i - NV)) * 3;
+        float* l = i < NV ? Lv + (size_t)h * LDN + i * 3 : Lj + (size_t)h * 192 + (i - NV) * 3;
+        if (MODE == 0) {
+            const float d[3] = {x[0] - J0[0], x[1] - J0[1], x[2] - J0[2]};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) l[c] = R[0 * 3 + c] * d[0] + R[1 * 3 + c] * d[1] + R[2 * 3 + c] * d[2];
+        } else if (i != NV) {                      // the wrist itself (joint 0) never moves
+            const float a[3] = {l[0], l[1], l[2]};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[c] = R[c * 3 + 0] * a[0] + R[c * 3 + 1] * a[1] + R[c * 3 + 2] * a[2] + J0[c];
+        }
+    }
+}
+
+// d loss / d orient = rodrigues_bwd( sum_points g (x) L ), added to the orient slots of the gradient rows
+__global__ void __launch_bounds__(RG_THREADS)
+k_rigid_bwd(int n, HandSrc src, const float* __restrict__ gverts, const float* __restrict__ gtips,
+            const float* __restrict__ gjoints, const float* __restrict__ Lv, const float* __restrict__ Lj,
+            float* __restrict__ params_grad) {
+    __shared__ float red[9][RG_THREADS / 32];
+    const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float M[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) M[i] = 0.f;
+    for (int i = tid; i < NV + NJ; i += RG_THREADS) {
+        float g[3];
+        const float* l;
+        if (i < NV) {
+            const float* gp = gverts + ((size_t)h * NV + i) * 3;
+            g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
+            const int tip = (i == 744) ? 0 : (i == 320) ? 1 : (i == 443) ? 2 : (i == 554) ? 3 : (i == 671) ? 4 : -1;
+            if (tip >= 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[c] += gtips[((size_t)h * 5 + tip) * 3 + c];
+            }
+            l = Lv + (size_t)h * LDN + i * 3;
+        } else {
+            const float* gp = gjoints + ((size_t)h * NJ + (i - NV)) * 3;
+            g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
+            l = Lj + (size_t)h * 192 + (i - NV) * 3;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) M[a * 3 + c] += g[a] * l[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        float v = M[i];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float dR[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < RG_THREADS / 32; ++w) v += red[i][w];
+            dR[i] = v;
+        }
+        float r[3], theta, R[9], dr[3];
+        root_rotation<true>(src, h, r, theta, R);
+        rodrigues_bwd(r, theta, dR, dr);
+        if (h & 1) { dr[1] = -dr[1]; dr[2] = -dr[2]; }
+        float* gr = params_grad + (size_t)(h >> 1) * PD + P_POSE + 48 * (h & 1);
+        gr[0] += dr[0]; gr[1] += dr[1]; gr[2] += dr[2];
+    }
+}
+
+int launch_rigid_prep(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    k_rigid_xform<0><<<n, RG_THREADS, 0, st>>>(n, src, verts, joints, Lv, Lj);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    k_rigid_xform<1><<<n, RG_THREADS, 0, st>>>(n, src, verts, joints, Lv, Lj);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips, const float* gjoints, const float* Lv,
+                     const float* Lj, float* params_grad, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    k_rigid_bwd<<<n, RG_THREADS, 0, st>>>(n, src, gverts, gtips, gjoints, Lv, Lj, params_grad);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
 // -------------------------------------------------------------------------------- launchers
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

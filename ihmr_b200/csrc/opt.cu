@@ -452,6 +452,8 @@ struct IterPlan {
     bool blend_bwd = true;    // blend contraction backward: pose / shape live
     int sdf_skip_grid = 0;    // stage that only moves the left hand rigidly: the right hand's samples
                               // carry no gradient, their loss part is needed at snapshots only
+    int rigid = 0;            // orientation-only stage: 1 = first iteration (generic forward, then cache the
+                              // root-local geometry), 2 = later iterations (x = R0 L + J0); backward is rigid in both
 };
 
 static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
@@ -463,6 +465,11 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
     p.mano_bwd = live_mano;
     p.blend_bwd = live_blend;
     p.sdf_skip_grid = (!live_mano && !snapshot) ? 2 : 0;
+    if (live_mano && !live_blend) {          // only the global orientations move (opt_default stage 1)
+        p.rigid = first ? 1 : 2;
+        p.mano_fwd = first;
+        p.mano_bwd = false;
+    }
     return p;
 }
 
@@ -479,10 +486,13 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     if (plan.blend_fwd && (rc = launch_blend_fwd(m, 2 * B, w.mano.X, w.mano.off, st))) return rc;
     IHMR_TICK(prof, 2);
     if (plan.mano_fwd && (rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st))) return rc;
+    // orientation-only stage: the root-local geometry lives in the (otherwise idle) gposed / dA buffers
+    if (plan.rigid == 1 && (rc = launch_rigid_prep(2 * B, src, w.verts, w.joints, w.mano.gposed, w.mano.dA, st))) return rc;
+    if (plan.rigid == 2 && (rc = launch_rigid_fwd(2 * B, src, w.verts, w.joints, w.mano.gposed, w.mano.dA, st))) return rc;
     IHMR_TICK(prof, 3);
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
-    sa.losses = w.col_loss; sa.gverts = plan.mano_bwd ? w.gverts : nullptr; sa.gshift = w.gshift;
+    sa.losses = w.col_loss; sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
     sa.grad_scale = stg->w_collision / (float)bs_norm;
     sa.skip_grid_mask = plan.sdf_skip_grid;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
@@ -497,6 +507,7 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     IHMR_TICK(prof, 6);
     if (plan.blend_bwd && (rc = launch_blend_bwd(m, 2 * B, w.mano.gposed, w.mano.dX, st))) return rc;
     IHMR_TICK(prof, 7);
+    if (plan.rigid && (rc = launch_rigid_bwd(2 * B, src, w.gverts, w.gtips, w.gjoints, w.mano.gposed, w.mano.dA, w.grad, st))) return rc;
     HandGrad hg;
     hg.params_grad = w.grad;
     if (plan.mano_bwd && (rc = launch_pose_bwd(m, 2 * B, src, w.mano.dA, w.gjoints, plan.blend_bwd ? w.mano.dX : nullptr, hg, st))) return rc;
