@@ -29,10 +29,12 @@ constexpr int SDF_WARPS = SDF_THREADS / 32;
 #define SDF_MIN_CTAS 3               // resident CTAs per SM the register allocation is held to
 #endif
 constexpr int SDF_SLOTS = 4;        // 4 x 256 >= 778 query vertices
-constexpr int PHI_CAP = 4096;       // voxels evaluated per pass (more voxels: further passes)
-constexpr int Q_CAP = 2048;         // queued candidates (overflow is processed in place)
+constexpr int PHI_CAP = 2048;       // voxels evaluated per pass (more voxels: further passes)
+constexpr int Q_CAP = 4096;         // queued candidates (overflow is processed in place)
 constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
-constexpr int P_CAP = 2048;         // queued (voxel, cluster) pairs of one distance band
+constexpr int P_CAP = 2048;         // queued (voxel, cluster) pairs of one chunk of voxels
+constexpr int V_CHUNK = 384;        // voxels per (A) round: ~3-5 pairs each in the inner band, so P_CAP rarely overflows
+constexpr int P_CHUNK = 320;        // pairs per (B) round: ~1/3 of their 32 faces pass, so Q_CAP rarely overflows
 #ifndef SDF_R_CELLS
 #define SDF_R_CELLS 2.5f
 #endif
@@ -55,18 +57,20 @@ struct __align__(16) SdfSmem {
     uint16_t far_list[PHI_CAP]; // voxels whose nearest face is beyond SDF_R
     uint32_t best[PHI_CAP];     // bit pattern of the best squared distance (>= 0: orders like uint); then phi
     uint32_t queue[Q_CAP];      // (voxel index << 16) | slot of the face in the cluster table
+    uint32_t pairs[P_CAP];      // (voxel index << 6) | cluster
     float cl_box[NCL * 6];      // bounding boxes of the static face clusters (lo xyz, hi xyz)
     uint8_t fbox8[NCL * 32 * 6];// per face (cluster-table order): box quantised outwards to 1/127.5, lo xyz hi xyz
     float red[64];
     float box[2][2][3];         // [hand][lo/hi][xyz]
     float shift[4];
     int scan_warp[SDF_WARPS];
-    uint32_t qn;
-    uint32_t pn[4];
+    uint32_t qn[2];             // queue fill, double buffered by round
+    uint32_t pn[3];             // pair fill, rotating by round (a round without pairs has no barrier of its own)
     int far_count;
 };
 
-__device__ __forceinline__ float voxel_center(int i) { return (2.0f * i + 1.0f - G) / G; }
+// (2i + 1 - G) / G; every intermediate is a small multiple of 1/G, so the fused form is exact too
+__device__ __forceinline__ float voxel_center(int i) { return fmaf((float)i, 2.0f / G, (1.0f - G) / G); }
 
 // ---- arithmetic contract shared with oracle/sdf_oracle.c (explicitly unfused) -----------
 __device__ __forceinline__ bool edge_side(const float* P, int i0, int i1, float qy, float qz, float& w) {
@@ -351,36 +355,44 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         __syncthreads();
 
         // ---- query vertices: normalised position, voxel corners, mark
+        // (the cell of a query vertex is recomputed at sampling time rather than kept in registers)
+        auto locate = [&](const float* p, float* fr, int* i0) -> bool {
+            // only vertices within one voxel of the grid hand's own box can touch a voxel that may be inside
+            // (no lower limit in x: behind the open wrist, voxels left of the mesh can have odd parity)
+            bool in = p[0] <= whi[0] && p[1] >= wlo[1] && p[1] <= whi[1] && p[2] >= wlo[2] && p[2] <= whi[2];
+            if (!in) return false;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float pn = (p[c] - cen[c]) / scale;
+                const float ix = ((pn + 1.0f) * G - 1.0f) * 0.5f;
+                const float fl = floorf(ix);
+                fr[c] = ix - fl;
+                // clamp before the int conversion: far-away vertices must not overflow
+                i0[c] = (int)fminf(fmaxf(fl, -2.0f), (float)G);
+                in = in && (i0[c] >= -1) && (i0[c] <= G - 1);
+            }
+            return in;
+        };
         float acc[SDF_SLOTS][4];
-        float fr[SDF_SLOTS][3];
-        int i0[SDF_SLOTS][3];
-        bool act[SDF_SLOTS];
+        uint32_t act = 0u;
         bool any = false;
+        float pq[SDF_SLOTS][3];              // all loads in flight before the first use
 #pragma unroll
         for (int sl = 0; sl < SDF_SLOTS; ++sl) {
             const int v = tid + sl * SDF_THREADS;
-            act[sl] = false;
+            pq[sl][0] = 3e30f; pq[sl][1] = 0.f; pq[sl][2] = 0.f;         // beyond whi[0]: rejected
+            if (v < NV) load_vert(o, v, pq[sl]);
+        }
+#pragma unroll
+        for (int sl = 0; sl < SDF_SLOTS; ++sl) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[sl][c] = 0.f;
-            if (v < NV) {
-                float p[3];
-                load_vert(o, v, p);
-                // only vertices within one voxel of the grid hand's own box can touch a voxel that may be inside
-                // (no lower limit in x: behind the open wrist, voxels left of the mesh can have odd parity)
-                bool in = p[0] <= whi[0] && p[1] >= wlo[1] && p[1] <= whi[1] && p[2] >= wlo[2] && p[2] <= whi[2];
-                if (!in) continue;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float pn = (p[c] - cen[c]) / scale;
-                    const float ix = ((pn + 1.0f) * G - 1.0f) * 0.5f;
-                    const float fl = floorf(ix);
-                    fr[sl][c] = ix - fl;
-                    // clamp before the int conversion: far-away vertices must not overflow
-                    i0[sl][c] = (int)fminf(fmaxf(fl, -2.0f), (float)G);
-                    in = in && (i0[sl][c] >= -1) && (i0[sl][c] <= G - 1);
-                }
-                act[sl] = in;
+            {
+                float fr[3];
+                int i0[3];
+                const bool in = locate(pq[sl], fr, i0);
                 if (in) {
+                    act |= 1u << sl;
                     // A voxel can only be inside (odd +x crossings) if its (y,z) lies within the
                     // mesh's (y,z) extent and its x is left of the mesh's largest x: other corners
                     // are certainly 0 and need not be marked.
@@ -388,13 +400,13 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy) {
-                            const int zc = i0[sl][2] + dz, yc = i0[sl][1] + dy;
+                            const int zc = i0[2] + dz, yc = i0[1] + dy;
                             if (zc < 0 || zc >= G || yc < 0 || yc >= G) continue;
                             const float yv = voxel_center(yc), zv = voxel_center(zc);
                             if (yv < tlo[1] || yv > thi[1] || zv < tlo[2] || zv > thi[2]) continue;
                             uint32_t bits = 0u;
-                            if (i0[sl][0] >= 0 && voxel_center(i0[sl][0]) <= thi[0]) bits |= 1u << i0[sl][0];
-                            if (i0[sl][0] + 1 < G && voxel_center(i0[sl][0] + 1) <= thi[0]) bits |= 1u << (i0[sl][0] + 1);
+                            if (i0[0] >= 0 && voxel_center(i0[0]) <= thi[0]) bits |= 1u << i0[0];
+                            if (i0[0] + 1 < G && voxel_center(i0[0] + 1) <= thi[0]) bits |= 1u << (i0[0] + 1);
                             if (bits) { any = true; atomicOr(&s.needed[zc * G + yc], bits); }
                         }
                 }
@@ -402,8 +414,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         }
         const bool any_block = __syncthreads_or(any);
         if (a.stats) {
-            const int nact = __syncthreads_count(act[0]) + __syncthreads_count(act[1]) + __syncthreads_count(act[2]) +
-                             __syncthreads_count(act[3]);
+            const int nact = __syncthreads_count(act & 1u) + __syncthreads_count(act & 2u) + __syncthreads_count(act & 4u) +
+                             __syncthreads_count(act & 8u);
             if (tid == 0) a.stats[b * 32 + 4 + h] = nact;
         }
         SDF_STAT(2)
@@ -423,7 +435,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             // ---- parity of the marked columns, two steps so that the ray tests run with full warps:
             //      (1) thread per face: lattice points inside its (y,z) box whose column is marked
             //          -> (face, column) items; (2) thread per item: the exact ray test
-            if (tid == 0) s.qn = 0u;
+            if (tid == 0) s.qn[0] = 0u;
             __syncthreads();
             auto ray_item = [&](int f, int col) {
                 const ushort4 id = f4[f];
@@ -435,27 +447,55 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 while (cnt > 0 && !(x > voxel_center(cnt - 1))) --cnt;
                 if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
             };
-            for (int f = tid; f < NF; f += SDF_THREADS) {
-                const ushort4 id = f4[f];
-                const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
-                const float ymin = fminf(A_[1], fminf(B_[1], C_[1])), ymax = fmaxf(A_[1], fmaxf(B_[1], C_[1]));
-                const float zmin = fminf(A_[2], fminf(B_[2], C_[2])), zmax = fmaxf(A_[2], fmaxf(B_[2], C_[2]));
-                // lattice points y_j = (2j+1-G)/G inside [ymin,ymax]
-                // (1e-3 of a cell absorbs the rounding of the index arithmetic; the ray test itself decides)
-                const int j0 = max(0, (int)ceilf((ymin * G + (G - 1)) * 0.5f - 1e-3f)), j1 = min(G - 1, (int)floorf((ymax * G + (G - 1)) * 0.5f + 1e-3f));
-                const int k0 = max(0, (int)ceilf((zmin * G + (G - 1)) * 0.5f - 1e-3f)), k1 = min(G - 1, (int)floorf((zmax * G + (G - 1)) * 0.5f + 1e-3f));
-                for (int k = k0; k <= k1; ++k)
-                    for (int j = j0; j <= j1; ++j) {
-                        const int col = k * G + j;
-                        if (s.needed[col] == 0u) continue;
-                        const uint32_t pos = atomicAdd(&s.qn, 1u);
-                        if (pos < Q_CAP) s.queue[pos] = ((uint32_t)f << 10) | (uint32_t)col;
-                        else ray_item(f, col);
+            for (int f0 = 0; f0 < NF; f0 += SDF_THREADS) {
+                const int f = f0 + tid;
+                int j0 = 0, j1 = -1, k0 = 0, k1 = -1;
+                if (f < NF) {
+                    const ushort4 id = f4[f];
+                    const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
+                    const float ymin = fminf(A_[1], fminf(B_[1], C_[1])), ymax = fmaxf(A_[1], fmaxf(B_[1], C_[1]));
+                    const float zmin = fminf(A_[2], fminf(B_[2], C_[2])), zmax = fmaxf(A_[2], fmaxf(B_[2], C_[2]));
+                    // lattice points y_j = (2j+1-G)/G inside [ymin,ymax]
+                    // (1e-3 of a cell absorbs the rounding of the index arithmetic; the ray test itself decides)
+                    j0 = max(0, (int)ceilf((ymin * G + (G - 1)) * 0.5f - 1e-3f)); j1 = min(G - 1, (int)floorf((ymax * G + (G - 1)) * 0.5f + 1e-3f));
+                    k0 = max(0, (int)ceilf((zmin * G + (G - 1)) * 0.5f - 1e-3f)); k1 = min(G - 1, (int)floorf((zmax * G + (G - 1)) * 0.5f + 1e-3f));
+                }
+                // Most faces cover at most 2 x 2 lattice points: those are handled with the warp converged and
+                // one queue reservation per warp and lattice slot; larger faces take the loop below.
+                const bool small = (j1 - j0 <= 1) && (k1 - k0 <= 1);
+#pragma unroll
+                for (int dk = 0; dk < 2; ++dk)
+#pragma unroll
+                    for (int dj = 0; dj < 2; ++dj) {
+                        const int k = k0 + dk, j = j0 + dj, col = k * G + j;
+                        const bool ok = small && k <= k1 && j <= j1 && s.needed[col & (G * G - 1)] != 0u;
+                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                        if (m == 0u) continue;
+                        const int leader = __ffs(m) - 1;
+                        uint32_t base = 0u;
+                        if (lane == leader) base = atomicAdd(&s.qn[0], (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (ok) {
+                            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                            if (pos < Q_CAP) s.queue[pos] = ((uint32_t)f << 10) | (uint32_t)col;
+                            else ray_item(f, col);
+                        }
                     }
+                if (!small) {
+                    for (int k = k0; k <= k1; ++k)
+                        for (int j = j0; j <= j1; ++j) {
+                            const int col = k * G + j;
+                            if (s.needed[col] == 0u) continue;
+                            const uint32_t pos = atomicAdd(&s.qn[0], 1u);
+                            if (pos < Q_CAP) s.queue[pos] = ((uint32_t)f << 10) | (uint32_t)col;
+                            else ray_item(f, col);
+                        }
+                }
             }
             __syncthreads();
             {
-                const int nq = min((int)s.qn, Q_CAP);
+                const int nq = min((int)s.qn[0], Q_CAP);
+                if (a.stats && tid == 0) a.stats[b * 32 + 21] += (int)s.qn[0];
                 for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) ray_item(s.queue[p2] >> 10, s.queue[p2] & 1023u);
             }
             __syncthreads();
@@ -469,6 +509,11 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 s.work[c] = wk;
                 cnt[i] = __popc(wk);
                 if (wk) atomicOr(&s.row_mask[c >> 5], 1u << (c & 31));
+            }
+            if (a.stats) {
+                int nm = 0;
+                for (int i = 0; i < 4; ++i) nm += __popc(s.needed[tid * 4 + i]);
+                atomicAdd(&a.stats[b * 32 + 20], nm);
             }
             total = block_scan_1024(cnt, excl, s.scan_warp);
 #pragma unroll
@@ -494,7 +539,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     }
                 }
                 for (int i = tid; i < nvox; i += SDF_THREADS) s.best[i] = 0x7f7fffffu;
-                if (tid == 0) { s.qn = 0u; s.far_count = 0; }
+                if (tid == 0) { s.qn[0] = 0u; s.qn[1] = 0u; s.pn[0] = 0u; s.pn[1] = 0u; s.pn[2] = 0u; s.far_count = 0; }
                 __syncthreads();
                 SDF_STAT(6)
                 // ---- nearest face of every voxel, bulk-synchronous and balanced (work is indexed by voxel):
@@ -537,65 +582,71 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                         for (int ax = 0; ax < 3; ++ax) { s.cl_box[c * 6 + ax] = lo[ax]; s.cl_box[c * 6 + 3 + ax] = hi[ax]; }
                     }
                 }
-                if (tid < 4) s.pn[tid] = 0u;
                 __syncthreads();
-                uint32_t* pairs = reinterpret_cast<uint32_t*>(s.far_list);      // far_list is free until the classification
-                static_assert(sizeof(s.far_list) >= P_CAP * sizeof(uint32_t), "pair queue aliases far_list");
                 constexpr float cell = 2.0f / G;
                 const float band_hi[3] = {(SDF_BAND0 * cell) * (SDF_BAND0 * cell), (SDF_BAND1 * cell) * (SDF_BAND1 * cell), SDF_R2};
+                int pa = 0, qb = 0;                  // fill counters of the current (A) / (B) round
                 for (int band = 0; band < 3; ++band) {
                     const float b_lo = band ? band_hi[band - 1] : 0.f, b_hi = band_hi[band];
-                    // (A) voxel x cluster.  A voxel whose best is below the previous band limit is final:
-                    //     every face closer than that limit sits in a cluster that was already processed.
-                    for (int i = tid; i < nvox * NCL; i += SDF_THREADS) {
-                        const int v = i / NCL, c = i - v * NCL;
-                        const float bv = __uint_as_float(s.best[v]);
-                        if (bv < b_lo) continue;
-                        float q[3];
-                        voxel_pos(s.worklist[v], q);
-                        const float* bx = s.cl_box + c * 6;
-                        float d2 = 0.f;
+                    for (int v0 = 0; v0 < nvox; v0 += V_CHUNK, pa = (pa == 2) ? 0 : pa + 1) {
+                        // (A) voxel x cluster.  A voxel whose best is below the previous band limit is final:
+                        //     every face closer than that limit sits in a cluster that was already processed.
+                        uint32_t* pn = &s.pn[pa];
+                        if (tid == 0) s.pn[(pa == 2) ? 0 : pa + 1] = 0u;   // read last two rounds ago, used next round
+                        const int nvc = min(V_CHUNK, nvox - v0);
+                        for (int i = tid; i < nvc * NCL; i += SDF_THREADS) {
+                            const int vl = i / NCL, c = i - vl * NCL, v = v0 + vl;
+                            const float bv = __uint_as_float(s.best[v]);
+                            if (bv < b_lo) continue;
+                            float q[3];
+                            voxel_pos(s.worklist[v], q);
+                            const float* bx = s.cl_box + c * 6;
+                            float d2 = 0.f;
 #pragma unroll
-                        for (int ax = 0; ax < 3; ++ax) {
-                            const float d = fmaxf(fmaxf(bx[ax] - q[ax], q[ax] - bx[3 + ax]), 0.f);
-                            d2 += d * d;
+                            for (int ax = 0; ax < 3; ++ax) {
+                                const float d = fmaxf(fmaxf(bx[ax] - q[ax], q[ax] - bx[3 + ax]), 0.f);
+                                d2 += d * d;
+                            }
+                            if (d2 < b_lo || d2 >= b_hi || d2 >= bv) continue;
+                            const uint32_t pos = atomicAdd(pn, 1u);
+                            if (pos < P_CAP) s.pairs[pos] = ((uint32_t)v << 6) | (uint32_t)c;
+                            else for (int l = 0; l < 32; ++l) if (cl_tri[c * 32 + l].w) pair_test(s, cl_tri, v, c * 32 + l);
                         }
-                        if (d2 < b_lo || d2 >= b_hi || d2 >= bv) continue;
-                        const uint32_t pos = atomicAdd(&s.pn[0], 1u);
-                        if (pos < P_CAP) pairs[pos] = ((uint32_t)v << 6) | (uint32_t)c;
-                        else for (int l = 0; l < 32; ++l) if (cl_tri[c * 32 + l].w) pair_test(s, cl_tri, v, c * 32 + l);
-                    }
-                    __syncthreads();
-                    // (B) pair x face of the cluster, quantised boxes (lower bound of the true box distance)
-                    const int np = min((int)s.pn[0], P_CAP);
-                    for (int jj = tid; jj < np * 32; jj += SDF_THREADS) {
-                        const uint32_t pr = pairs[jj >> 5];
-                        const int v = pr >> 6, slot = (pr & 63u) * 32 + (jj & 31);
-                        const uint8_t* fb = s.fbox8 + slot * 6;
-                        float q[3];
-                        voxel_pos(s.worklist[v], q);
-                        float d2 = 0.f;
+                        __syncthreads();
+                        const int np = min((int)*pn, P_CAP);
+                        if (a.stats && tid == 0) { a.stats[b * 32 + 6] += (int)*pn; a.stats[b * 32 + 22 + 2 * band] += (int)*pn; }
+                        for (int p0 = 0; p0 < np; p0 += P_CHUNK, qb ^= 1) {
+                            // (B) pair x face of the cluster, quantised boxes (lower bound of the true box distance)
+                            uint32_t* qn = &s.qn[qb];
+                            const int npc = min(P_CHUNK, np - p0);
+                            for (int jj = tid; jj < npc * 32; jj += SDF_THREADS) {
+                                const uint32_t pr = s.pairs[p0 + (jj >> 5)];
+                                const int v = pr >> 6, slot = (pr & 63u) * 32 + (jj & 31);
+                                const uint8_t* fb = s.fbox8 + slot * 6;
+                                float q[3];
+                                voxel_pos(s.worklist[v], q);
+                                float d2 = 0.f;
 #pragma unroll
-                        for (int ax = 0; ax < 3; ++ax) {
-                            const float lo = fb[ax] * (1.0f / 127.5f) - 1.0f, hi = fb[3 + ax] * (1.0f / 127.5f) - 1.0f;
-                            const float d = fmaxf(fmaxf(lo - q[ax], q[ax] - hi), 0.f);
-                            d2 += d * d;
+                                for (int ax = 0; ax < 3; ++ax) {
+                                    const float lo = fb[ax] * (1.0f / 127.5f) - 1.0f, hi = fb[3 + ax] * (1.0f / 127.5f) - 1.0f;
+                                    const float d = fmaxf(fmaxf(lo - q[ax], q[ax] - hi), 0.f);
+                                    d2 += d * d;
+                                }
+                                // a face whose box is farther than R or than the voxel's best cannot matter
+                                if (fb[0] > fb[3] || d2 >= SDF_R2 || d2 >= __uint_as_float(s.best[v])) continue;
+                                const uint32_t pos = atomicAdd(qn, 1u);
+                                if (pos < Q_CAP) s.queue[pos] = ((uint32_t)v << 16) | (uint32_t)slot;
+                                else pair_test(s, cl_tri, v, slot);          // queue full: test in place
+                            }
+                            __syncthreads();
+                            // (C) exact tests
+                            const int nq = min((int)*qn, Q_CAP);
+                            if (tid == 0) s.qn[qb ^ 1] = 0u;              // last read before this round's (B)
+                            if (a.stats && tid == 0) { a.stats[b * 32 + 7] += (int)*qn; a.stats[b * 32 + 23 + 2 * band] += (int)*qn; }
+                            for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) pair_test(s, cl_tri, s.queue[p2] >> 16, s.queue[p2] & 0xffffu);
+                            __syncthreads();
                         }
-                        // a face whose box is farther than R or than the voxel's best cannot matter
-                        if (fb[0] > fb[3] || d2 >= SDF_R2 || d2 >= __uint_as_float(s.best[v])) continue;
-                        const uint32_t pos = atomicAdd(&s.qn, 1u);
-                        if (pos < Q_CAP) s.queue[pos] = ((uint32_t)v << 16) | (uint32_t)slot;
-                        else pair_test(s, cl_tri, v, slot);          // queue full: test in place
                     }
-                    __syncthreads();
-                    // (C) exact tests
-                    {
-                        const int nq = min((int)s.qn, Q_CAP);
-                        for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) pair_test(s, cl_tri, s.queue[p2] >> 16, s.queue[p2] & 0xffffu);
-                    }
-                    __syncthreads();
-                    if (tid == 0) { s.qn = 0u; s.pn[0] = 0u; }
-                    __syncthreads();
                 }
                 SDF_STAT(7)
                 // ---- certified voxels get phi; the others (nearest face beyond R) go to the far search
@@ -619,15 +670,19 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 // ---- trilinear sample + gradient (grid_sampler_3d fwd/bwd, align_corners=False, zeros)
 #pragma unroll
                 for (int sl = 0; sl < SDF_SLOTS; ++sl) {
-                    if (!act[sl]) continue;
-                    const float tx = fr[sl][0], ty = fr[sl][1], tz = fr[sl][2];
+                    if (!((act >> sl) & 1u)) continue;
+                    float fr[3], pv[3];
+                    int i0[3];
+                    load_vert(o, tid + sl * SDF_THREADS, pv);
+                    locate(pv, fr, i0);
+                    const float tx = fr[0], ty = fr[1], tz = fr[2];
 #pragma unroll
                     for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                             for (int dx = 0; dx < 2; ++dx) {
-                                const int xc = i0[sl][0] + dx, yc = i0[sl][1] + dy, zc = i0[sl][2] + dz;
+                                const int xc = i0[0] + dx, yc = i0[1] + dy, zc = i0[2] + dz;
                                 if (xc < 0 || xc >= G || yc < 0 || yc >= G || zc < 0 || zc >= G) continue;
                                 const int c = zc * G + yc;
                                 const uint32_t wk = s.work[c];
@@ -690,11 +745,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
 
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     if (B <= 0) return IHMR_OK;
-    static bool configured = false;
-    if (!configured) {
-        IHMR_CUDA_OK(cudaFuncSetAttribute(k_sdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SdfSmem)));
-        configured = true;
-    }
+    static unsigned long long configured = 0ull;
+    if (int rc = ensure_dynamic_smem(k_sdf, sizeof(SdfSmem), configured)) return rc;
     k_sdf<<<B, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, m->faces[0], m->faces[1],
                                                     reinterpret_cast<const ushort4*>(m->cl_tri[0]),
                                                     reinterpret_cast<const ushort4*>(m->cl_tri[1]));

@@ -26,7 +26,9 @@ names = ["evalR", "farR", "evalL", "farL", "activeQ(gridR)", "activeQ(gridL)", "
 for i, n in enumerate(names):
     c = st[:, i]
     print(f"{n:>16}: mean {c.mean():8.1f}  p50 {np.percentile(c,50):7.0f} p90 {np.percentile(c,90):7.0f} p99 {np.percentile(c,99):7.0f} max {c.max():7.0f}  nonzero {np.mean(c>0)*100:5.1f}%")
-for i, n in [(20, "visitsR"), (21, "visitsL"), (22, "testsR"), (23, "testsL")]:
+names[6:8] = ["pairs", "candidates"]
+for i, n in [(6, "pairs"), (7, "candidates"), (20, "marked"), (21, "ray items"), (22, "pairs b0"), (23, "cands b0"), (24, "pairs b1"), (25, "cands b1"),
+             (26, "pairs b2"), (27, "cands b2")]:
     c = st[:, i]
     print(f"{n:>16}: mean {c.mean():9.1f}  p50 {np.percentile(c,50):7.0f} p90 {np.percentile(c,90):8.0f} p99 {np.percentile(c,99):8.0f} max {c.max():8.0f}")
 ph = ["-", "bbox", "mark", "normalise", "parity", "scan", "worklist", "candidates+tests", "classify+far", "sample", "outputs", "-"]
