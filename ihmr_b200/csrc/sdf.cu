@@ -23,31 +23,57 @@
 namespace ihmr {
 
 constexpr int G = 32;
-constexpr int SDF_THREADS = 256;
-constexpr int SDF_WARPS = SDF_THREADS / 32;
-#ifndef SDF_MIN_CTAS
-#define SDF_MIN_CTAS 3               // resident CTAs per SM the register allocation is held to
+#ifndef SDF_NTHREADS
+#define SDF_NTHREADS 512             // measured: 512 x 2 CTAs/SM beats 256 x 3 and 256 x 4
 #endif
-constexpr int SDF_SLOTS = 4;        // 4 x 256 >= 778 query vertices
-constexpr int PHI_CAP = 2048;       // voxels evaluated per pass (more voxels: further passes)
-constexpr int Q_CAP = 4096;         // queued candidates (overflow is processed in place)
+constexpr int SDF_THREADS = SDF_NTHREADS;
+constexpr int SDF_WARPS = SDF_THREADS / 32;
+constexpr int SDF_CPT = G * G / SDF_THREADS;   // (z,y) columns per thread in the scans
+#ifndef SDF_MIN_CTAS
+#define SDF_MIN_CTAS 2               // resident CTAs per SM the register allocation is held to
+#endif
+constexpr int SDF_SLOTS = (NV + SDF_THREADS - 1) / SDF_THREADS;   // query vertices per thread
 constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
-constexpr int P_CAP = 2048;         // queued (voxel, cluster) pairs of one chunk of voxels
-constexpr int V_CHUNK = 384;        // voxels per (A) round: ~3-5 pairs each in the inner band, so P_CAP rarely overflows
-constexpr int P_CHUNK = 320;        // pairs per (B) round: ~1/3 of their 32 faces pass, so Q_CAP rarely overflows
+#if SDF_MIN_CTAS >= 4               // <= 56 KB of shared memory per CTA
+constexpr int PHI_CAP = 1024;       // voxels evaluated per pass (more voxels: further passes)
+constexpr int Q_CAP = 2048;         // queued candidates (overflow is processed in place)
+constexpr int P_CAP = 1024;         // queued (voxel, cluster) pairs of one chunk of voxels
+constexpr int V_CHUNK = 224;        // voxels per (A) round: ~3-5 pairs each in the inner band, so P_CAP rarely overflows
+constexpr int P_CHUNK = 160;        // pairs per (B) round: ~1/3 of their 32 faces pass, so Q_CAP rarely overflows
+#elif SDF_MIN_CTAS == 3             // <= 75 KB
+constexpr int PHI_CAP = 2048;
+constexpr int Q_CAP = 4096;
+constexpr int P_CAP = 1536;
+constexpr int V_CHUNK = 320;
+constexpr int P_CHUNK = 320;
+#else                               // <= 112 KB
+constexpr int PHI_CAP = 2048;
+constexpr int Q_CAP = 6144;
+constexpr int P_CAP = 3072;
+constexpr int V_CHUNK = 640;
+constexpr int P_CHUNK = 480;
+#endif
 #ifndef SDF_R_CELLS
 #define SDF_R_CELLS 2.5f
 #endif
-#ifndef SDF_BAND0
-#define SDF_BAND0 0.35f
+// The nearest-face search works on boxes quantised to Q8 = 1/128 of the normalised cube (1/8 voxel):
+// voxel centres are the integers 8i + 4, box distances are exact integers.
+#ifndef SDF_SHELL
+#define SDF_SHELL 0
 #endif
-#ifndef SDF_BAND1
-#define SDF_BAND1 1.0f
+#ifndef SDF_T0
+#define SDF_T0 8                     // squared radius of round 0 in Q8 units (0.35 voxel)
 #endif
-constexpr float SDF_R = SDF_R_CELLS * (2.0f / G);   // candidate radius of the banded search, in voxels
-constexpr float SDF_R2 = SDF_R * SDF_R;
+#ifndef SDF_T1
+#define SDF_T1 64                    // round 1 (1 voxel); round 2 reaches R
+#endif
+constexpr int SDF_R_Q8 = (int)(SDF_R_CELLS * 8.0f);
+constexpr int SDF_R2_Q8 = SDF_R_Q8 * SDF_R_Q8;
+constexpr float Q8_TO_D2 = 1.0f / 16384.0f;         // Q8 units squared -> normalised units squared
+constexpr float SDF_R2 = SDF_R2_Q8 * Q8_TO_D2;      // squared radius the rounds certify
 
 struct __align__(16) SdfSmem {
+    float V[2 * NV * 3];        // both hands as stored (one TMA bulk copy, 18,672 B)
     float U[NV * 3];            // normalised grid-hand vertices
     uint32_t needed[G * G];     // marked voxels per (z,y) column
     uint32_t work[G * G];       // parity bits, then marked & inside
@@ -58,8 +84,9 @@ struct __align__(16) SdfSmem {
     uint32_t best[PHI_CAP];     // bit pattern of the best squared distance (>= 0: orders like uint); then phi
     uint32_t queue[Q_CAP];      // (voxel index << 16) | slot of the face in the cluster table
     uint32_t pairs[P_CAP];      // (voxel index << 6) | cluster
-    float cl_box[NCL * 6];      // bounding boxes of the static face clusters (lo xyz, hi xyz)
-    uint8_t fbox8[NCL * 32 * 6];// per face (cluster-table order): box quantised outwards to 1/127.5, lo xyz hi xyz
+    uint2 cl_box[NCL];          // union of the cluster's face boxes, same packing
+    uint2 fbox[NCL * 32];       // per face (cluster-table order): box quantised outwards to Q8;
+                                // .x = lo x | y << 8 | z << 16 | valid << 24, .y = hi x | y << 8 | z << 16
     float red[64];
     float box[2][2][3];         // [hand][lo/hi][xyz]
     float shift[4];
@@ -67,6 +94,7 @@ struct __align__(16) SdfSmem {
     uint32_t qn[2];             // queue fill, double buffered by round
     uint32_t pn[3];             // pair fill, rotating by round (a round without pairs has no barrier of its own)
     int far_count;
+    unsigned long long bar;     // mbarrier of the bulk copy
 };
 
 // (2i + 1 - G) / G; every intermediate is a small multiple of 1/G, so the fused form is exact too
@@ -149,22 +177,24 @@ __device__ __forceinline__ void block_sum4(float* v, int nval, float* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = 0; i < nval; ++i) {
         float s = warp_sum(v[i]);
-        if (lane == 0) red[i * 8 + warp] = s;
+        if (lane == 0) red[i * SDF_WARPS + warp] = s;
     }
     __syncthreads();
     for (int i = 0; i < nval; ++i) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < SDF_WARPS; ++w) s += red[i * 8 + w];
+        for (int w = 0; w < SDF_WARPS; ++w) s += red[i * SDF_WARPS + w];
         v[i] = s;
     }
     __syncthreads();
 }
 
-// exclusive scan of 1024 counts, 4 consecutive entries per thread; returns total
-__device__ __forceinline__ int block_scan_1024(const int (&cnt)[4], int (&excl)[4], int* scan_warp) {
+// exclusive scan of 1024 counts, SDF_CPT consecutive entries per thread; returns total
+__device__ __forceinline__ int block_scan_1024(const int (&cnt)[SDF_CPT], int (&excl)[SDF_CPT], int* scan_warp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int local = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    int local = 0;
+#pragma unroll
+    for (int i = 0; i < SDF_CPT; ++i) local += cnt[i];
     int inc = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -181,9 +211,21 @@ __device__ __forceinline__ int block_scan_1024(const int (&cnt)[4], int (&excl)[
     }
     int run = base + inc - local;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { excl[i] = run; run += cnt[i]; }
+    for (int i = 0; i < SDF_CPT; ++i) { excl[i] = run; run += cnt[i]; }
     __syncthreads();
     return total;
+}
+
+// squared distance, in Q8 units, from the voxel centre (qx,qy,qz) to a packed box
+__device__ __forceinline__ int qbox_d2(uint2 bx, int qx, int qy, int qz) {
+    const int lx = bx.x & 255, ly = (bx.x >> 8) & 255, lz = (bx.x >> 16) & 255;
+    const int hx = bx.y & 255, hy = (bx.y >> 8) & 255, hz = (bx.y >> 16) & 255;
+    const int dx = max(max(lx - qx, qx - hx), 0), dy = max(max(ly - qy, qy - hy), 0), dz = max(max(lz - qz, qz - hz), 0);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ void voxel_q8(int code, int& qx, int& qy, int& qz) {
+    qx = ((code << 3) & 0xf8) | 4; qy = ((code >> 2) & 0xf8) | 4; qz = ((code >> 7) & 0xf8) | 4;
 }
 
 __device__ __forceinline__ void voxel_pos(int code, float* q) {
@@ -208,21 +250,14 @@ __device__ __forceinline__ float eval_voxel_far(const SdfSmem& s, const ushort4*
                                                 float best, int lane) {
     float q[3];
     voxel_pos(code, q);
-    float lb[2];
+    int qx, qy, qz;
+    voxel_q8(code, qx, qy, qz);
+    float lb[2];                         // lower bounds: the quantised boxes contain the true ones
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         const int c = lane + 32 * t;
         lb[t] = 1e30f;
-        if (c < NCL) {
-            const float* bx = s.cl_box + c * 6;
-            float d2 = 0.f;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float d = fmaxf(fmaxf(bx[a] - q[a], q[a] - bx[3 + a]), 0.f);
-                d2 += d * d;
-            }
-            lb[t] = d2;
-        }
+        if (c < NCL) lb[t] = (float)qbox_d2(s.cl_box[c], qx, qy, qz) * Q8_TO_D2;
     }
     for (int it = 0; it < NCL; ++it) {
         float m = fminf(lb[0], lb[1]);
@@ -260,7 +295,17 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
     const int b = blockIdx.x;
     const bool xform = (a.joints != nullptr);
 
+    // Both hands of the frame are staged once by the TMA engine (one 1-D bulk copy completing on an
+    // mbarrier); every later phase reads them from shared memory.
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar);
     if (tid == 0) {
+        constexpr uint32_t V_BYTES = 2 * NV * 3 * sizeof(float);
+        static_assert(V_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(V_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(s.V)), "l"(a.verts + (size_t)b * (2 * NV * 3)), "r"(V_BYTES), "r"(bar) : "memory");
         float sh[3] = {0.f, 0.f, 0.f};
         if (xform) {
             const float* jr = a.joints + ((size_t)b * 2 + 0) * 48;
@@ -274,8 +319,17 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
     }
     __syncthreads();
     const float shx = s.shift[0], shy = s.shift[1], shz = s.shift[2];
+    {
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        } while (!done);
+    }
     auto load_vert = [&](int hand, int v, float* out) {
-        const float* p = a.verts + (((size_t)b * 2 + hand) * NV + v) * 3;
+        const float* p = s.V + (hand * NV + v) * 3;
         out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
         if (xform && hand == 1) { out[0] = -out[0] + shx; out[1] += shy; out[2] += shz; }
     };
@@ -308,12 +362,12 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
                     hgh = fmaxf(hgh, __shfl_xor_sync(0xffffffffu, hgh, o));
                 }
-                if (lane == 0) { scratch[(hnd * 3 + c) * 16 + warp] = l; scratch[(hnd * 3 + c) * 16 + 8 + warp] = hgh; }
+                if (lane == 0) { scratch[(hnd * 3 + c) * 2 * SDF_WARPS + warp] = l; scratch[(hnd * 3 + c) * 2 * SDF_WARPS + SDF_WARPS + warp] = hgh; }
             }
         __syncthreads();
         if (tid < 6) {
             float l = 1e30f, hgh = -1e30f;
-            for (int w = 0; w < SDF_WARPS; ++w) { l = fminf(l, scratch[tid * 16 + w]); hgh = fmaxf(hgh, scratch[tid * 16 + 8 + w]); }
+            for (int w = 0; w < SDF_WARPS; ++w) { l = fminf(l, scratch[tid * 2 * SDF_WARPS + w]); hgh = fmaxf(hgh, scratch[tid * 2 * SDF_WARPS + SDF_WARPS + w]); }
             s.box[tid / 3][0][tid % 3] = l;
             s.box[tid / 3][1][tid % 3] = hgh;
         }
@@ -414,8 +468,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         }
         const bool any_block = __syncthreads_or(any);
         if (a.stats) {
-            const int nact = __syncthreads_count(act & 1u) + __syncthreads_count(act & 2u) + __syncthreads_count(act & 4u) +
-                             __syncthreads_count(act & 8u);
+            int nact = 0;
+            for (int sl = 0; sl < SDF_SLOTS; ++sl) nact += __syncthreads_count((act >> sl) & 1u);
             if (tid == 0) a.stats[b * 32 + 4 + h] = nact;
         }
         SDF_STAT(2)
@@ -461,35 +515,41 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     k0 = max(0, (int)ceilf((zmin * G + (G - 1)) * 0.5f - 1e-3f)); k1 = min(G - 1, (int)floorf((zmax * G + (G - 1)) * 0.5f + 1e-3f));
                 }
                 // Most faces cover at most 2 x 2 lattice points: those are handled with the warp converged and
-                // one queue reservation per warp and lattice slot; larger faces take the loop below.
+                // one queue reservation per warp and lattice slot; the lattice box of a larger face is spread
+                // over the lanes of its warp.
+                auto push = [&](bool ok, int face, int col) {          // warp-converged
+                    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                    if (m == 0u) return;
+                    const int leader = __ffs(m) - 1;
+                    uint32_t base = 0u;
+                    if (lane == leader) base = atomicAdd(&s.qn[0], (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (ok) {
+                        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < Q_CAP) s.queue[pos] = ((uint32_t)face << 10) | (uint32_t)col;
+                        else ray_item(face, col);
+                    }
+                };
                 const bool small = (j1 - j0 <= 1) && (k1 - k0 <= 1);
 #pragma unroll
                 for (int dk = 0; dk < 2; ++dk)
 #pragma unroll
                     for (int dj = 0; dj < 2; ++dj) {
                         const int k = k0 + dk, j = j0 + dj, col = k * G + j;
-                        const bool ok = small && k <= k1 && j <= j1 && s.needed[col & (G * G - 1)] != 0u;
-                        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                        if (m == 0u) continue;
-                        const int leader = __ffs(m) - 1;
-                        uint32_t base = 0u;
-                        if (lane == leader) base = atomicAdd(&s.qn[0], (uint32_t)__popc(m));
-                        base = __shfl_sync(0xffffffffu, base, leader);
-                        if (ok) {
-                            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                            if (pos < Q_CAP) s.queue[pos] = ((uint32_t)f << 10) | (uint32_t)col;
-                            else ray_item(f, col);
-                        }
+                        push(small && k <= k1 && j <= j1 && s.needed[col & (G * G - 1)] != 0u, f, col);
                     }
-                if (!small) {
-                    for (int k = k0; k <= k1; ++k)
-                        for (int j = j0; j <= j1; ++j) {
-                            const int col = k * G + j;
-                            if (s.needed[col] == 0u) continue;
-                            const uint32_t pos = atomicAdd(&s.qn[0], 1u);
-                            if (pos < Q_CAP) s.queue[pos] = ((uint32_t)f << 10) | (uint32_t)col;
-                            else ray_item(f, col);
-                        }
+                uint32_t bigm = __ballot_sync(0xffffffffu, !small);
+                while (bigm) {
+                    const int src = __ffs(bigm) - 1;
+                    bigm &= bigm - 1u;
+                    const int fj0 = __shfl_sync(0xffffffffu, j0, src), fj1 = __shfl_sync(0xffffffffu, j1, src);
+                    const int fk0 = __shfl_sync(0xffffffffu, k0, src), fk1 = __shfl_sync(0xffffffffu, k1, src);
+                    const int ff = __shfl_sync(0xffffffffu, f, src);
+                    const int nj = fj1 - fj0 + 1, npts = nj * (fk1 - fk0 + 1);
+                    for (int t0 = 0; t0 < npts; t0 += 32) {
+                        const int t = t0 + lane, dk = t / nj, col = (fk0 + dk) * G + fj0 + (t - dk * nj);
+                        push(t < npts && s.needed[col & (G * G - 1)] != 0u, ff, col);
+                    }
                 }
             }
             __syncthreads();
@@ -501,10 +561,10 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             __syncthreads();
             SDF_STAT(4)
             // ---- marked & inside, prefix offsets, per-row column masks
-            int cnt[4], excl[4];
+            int cnt[SDF_CPT], excl[SDF_CPT];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = tid * 4 + i;
+            for (int i = 0; i < SDF_CPT; ++i) {
+                const int c = tid * SDF_CPT + i;
                 const uint32_t wk = s.needed[c] & s.work[c];
                 s.work[c] = wk;
                 cnt[i] = __popc(wk);
@@ -512,12 +572,12 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             }
             if (a.stats) {
                 int nm = 0;
-                for (int i = 0; i < 4; ++i) nm += __popc(s.needed[tid * 4 + i]);
+                for (int i = 0; i < SDF_CPT; ++i) nm += __popc(s.needed[tid * SDF_CPT + i]);
                 atomicAdd(&a.stats[b * 32 + 20], nm);
             }
             total = block_scan_1024(cnt, excl, s.scan_warp);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) s.coloff[tid * 4 + i] = (uint16_t)excl[i];
+            for (int i = 0; i < SDF_CPT; ++i) s.coloff[tid * SDF_CPT + i] = (uint16_t)excl[i];
             run = total > 0;
             SDF_STAT(5)
         }
@@ -527,8 +587,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 const int pass1 = min(total, pass0 + PHI_CAP);
                 const int nvox = pass1 - pass0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = tid * 4 + i;
+                for (int i = 0; i < SDF_CPT; ++i) {
+                    const int c = tid * SDF_CPT + i;
                     uint32_t wk = s.work[c];
                     int idx = s.coloff[c];
                     while (wk) {
@@ -542,55 +602,51 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 if (tid == 0) { s.qn[0] = 0u; s.qn[1] = 0u; s.pn[0] = 0u; s.pn[1] = 0u; s.pn[2] = 0u; s.far_count = 0; }
                 __syncthreads();
                 SDF_STAT(6)
-                // ---- nearest face of every voxel, bulk-synchronous and balanced (work is indexed by voxel):
-                //   (0) per cluster of <= 32 faces (static, spatially sorted): bounding box; per face: its
-                //       bounding box quantised outwards to 1/8 voxel (6 bytes, conservative)
-                //   for each distance band (< 0.35, < 1.0, < 2.5 voxels; measured best of five settings), nearest first:
-                //     (A) one thread per (voxel, cluster): box distance inside the band and below the voxel's
-                //         best -> (voxel, cluster) pairs; voxels whose best is below the band are final
-                //     (B) one thread per (pair, face of the cluster): quantised face-box distance against R
-                //         and the voxel's best -> (voxel, face) candidates
-                //     (C) one thread per candidate: exact point-triangle test, atomicMin into the voxel
-                //   Processing the bands in order makes (B) reject most faces of the outer bands.
+                // ---- nearest face of every voxel, bulk-synchronous and balanced (work is indexed by voxel)
+                //   (0) per face (static clusters of <= 32, spatially sorted): bounding box quantised outwards
+                //       to Q8; per cluster: the union of its face boxes
                 for (int c = warp; c < NCL; c += SDF_WARPS) {
                     const ushort4 id = cl_tri[c * 32 + lane];
-                    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-                    uint8_t* fb = s.fbox8 + (c * 32 + lane) * 6;
+                    int lo[3] = {255, 255, 255}, hi[3] = {0, 0, 0};
                     if (id.w) {
                         const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
 #pragma unroll
                         for (int ax = 0; ax < 3; ++ax) {
-                            lo[ax] = fminf(A_[ax], fminf(B_[ax], C_[ax]));
-                            hi[ax] = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
-                            fb[ax] = (uint8_t)max(0, min(255, (int)floorf((lo[ax] + 1.0f) * 127.5f)));
-                            fb[3 + ax] = (uint8_t)max(0, min(255, (int)ceilf((hi[ax] + 1.0f) * 127.5f)));
+                            const float l = fminf(A_[ax], fminf(B_[ax], C_[ax])), hgh = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
+                            lo[ax] = max(0, min(255, (int)floorf((l + 1.0f) * 128.0f - 1e-3f)));
+                            hi[ax] = max(0, min(255, (int)ceilf((hgh + 1.0f) * 128.0f + 1e-3f)));
                         }
-                    } else {
-#pragma unroll
-                        for (int ax = 0; ax < 3; ++ax) { fb[ax] = 255; fb[3 + ax] = 0; }
                     }
+                    s.fbox[c * 32 + lane] = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16) | (id.w ? 1u << 24 : 0u),
+                                                       (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16));
 #pragma unroll
                     for (int ax = 0; ax < 3; ++ax) {
 #pragma unroll
                         for (int sft = 16; sft >= 1; sft >>= 1) {
-                            lo[ax] = fminf(lo[ax], __shfl_xor_sync(0xffffffffu, lo[ax], sft));
-                            hi[ax] = fmaxf(hi[ax], __shfl_xor_sync(0xffffffffu, hi[ax], sft));
+                            lo[ax] = min(lo[ax], __shfl_xor_sync(0xffffffffu, lo[ax], sft));
+                            hi[ax] = max(hi[ax], __shfl_xor_sync(0xffffffffu, hi[ax], sft));
                         }
                     }
-                    if (lane == 0) {
-#pragma unroll
-                        for (int ax = 0; ax < 3; ++ax) { s.cl_box[c * 6 + ax] = lo[ax]; s.cl_box[c * 6 + 3 + ax] = hi[ax]; }
-                    }
+                    if (lane == 0)
+                        s.cl_box[c] = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16) | (1u << 24),
+                                                 (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16));
                 }
                 __syncthreads();
-                constexpr float cell = 2.0f / G;
-                const float band_hi[3] = {(SDF_BAND0 * cell) * (SDF_BAND0 * cell), (SDF_BAND1 * cell) * (SDF_BAND1 * cell), SDF_R2};
+                // Rounds of growing radius T_k (squared, Q8 units).  After round k every face whose quantised box
+                // is closer than T_k has been tested against every voxel still open, or was rejected by that
+                // voxel's best at the time (it cannot be nearer then): a voxel whose best is below T_k is final.
+                //   (A) thread per (open voxel, cluster): cluster box closer than T_k and than the voxel's best
+                //       -> (voxel, cluster) pairs.  The cluster box is the union of the face boxes, so it is
+                //       never farther than any of them.
+                //   (B) thread per (pair, face of the cluster): face box in the shell [T_{k-1}, T_k) and closer
+                //       than the voxel's best -> (voxel, face) candidates (inner shells were done in earlier rounds)
+                //   (C) thread per candidate: exact point-triangle test, atomicMin into the voxel
+                const int t2[4] = {0, SDF_T0, SDF_T1, SDF_R2_Q8};
                 int pa = 0, qb = 0;                  // fill counters of the current (A) / (B) round
                 for (int band = 0; band < 3; ++band) {
-                    const float b_lo = band ? band_hi[band - 1] : 0.f, b_hi = band_hi[band];
+                    const int t_lo = t2[band], t_hi = t2[band + 1];
+                    const float b_lo = (float)t_lo * Q8_TO_D2;
                     for (int v0 = 0; v0 < nvox; v0 += V_CHUNK, pa = (pa == 2) ? 0 : pa + 1) {
-                        // (A) voxel x cluster.  A voxel whose best is below the previous band limit is final:
-                        //     every face closer than that limit sits in a cluster that was already processed.
                         uint32_t* pn = &s.pn[pa];
                         if (tid == 0) s.pn[(pa == 2) ? 0 : pa + 1] = 0u;   // read last two rounds ago, used next round
                         const int nvc = min(V_CHUNK, nvox - v0);
@@ -598,16 +654,10 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                             const int vl = i / NCL, c = i - vl * NCL, v = v0 + vl;
                             const float bv = __uint_as_float(s.best[v]);
                             if (bv < b_lo) continue;
-                            float q[3];
-                            voxel_pos(s.worklist[v], q);
-                            const float* bx = s.cl_box + c * 6;
-                            float d2 = 0.f;
-#pragma unroll
-                            for (int ax = 0; ax < 3; ++ax) {
-                                const float d = fmaxf(fmaxf(bx[ax] - q[ax], q[ax] - bx[3 + ax]), 0.f);
-                                d2 += d * d;
-                            }
-                            if (d2 < b_lo || d2 >= b_hi || d2 >= bv) continue;
+                            int qx, qy, qz;
+                            voxel_q8(s.worklist[v], qx, qy, qz);
+                            const int d2 = qbox_d2(s.cl_box[c], qx, qy, qz);
+                            if ((!SDF_SHELL && d2 < t_lo) || d2 >= t_hi || (float)d2 * Q8_TO_D2 >= bv) continue;
                             const uint32_t pos = atomicAdd(pn, 1u);
                             if (pos < P_CAP) s.pairs[pos] = ((uint32_t)v << 6) | (uint32_t)c;
                             else for (int l = 0; l < 32; ++l) if (cl_tri[c * 32 + l].w) pair_test(s, cl_tri, v, c * 32 + l);
@@ -616,30 +666,21 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                         const int np = min((int)*pn, P_CAP);
                         if (a.stats && tid == 0) { a.stats[b * 32 + 6] += (int)*pn; a.stats[b * 32 + 22 + 2 * band] += (int)*pn; }
                         for (int p0 = 0; p0 < np; p0 += P_CHUNK, qb ^= 1) {
-                            // (B) pair x face of the cluster, quantised boxes (lower bound of the true box distance)
                             uint32_t* qn = &s.qn[qb];
                             const int npc = min(P_CHUNK, np - p0);
                             for (int jj = tid; jj < npc * 32; jj += SDF_THREADS) {
                                 const uint32_t pr = s.pairs[p0 + (jj >> 5)];
                                 const int v = pr >> 6, slot = (pr & 63u) * 32 + (jj & 31);
-                                const uint8_t* fb = s.fbox8 + slot * 6;
-                                float q[3];
-                                voxel_pos(s.worklist[v], q);
-                                float d2 = 0.f;
-#pragma unroll
-                                for (int ax = 0; ax < 3; ++ax) {
-                                    const float lo = fb[ax] * (1.0f / 127.5f) - 1.0f, hi = fb[3 + ax] * (1.0f / 127.5f) - 1.0f;
-                                    const float d = fmaxf(fmaxf(lo - q[ax], q[ax] - hi), 0.f);
-                                    d2 += d * d;
-                                }
-                                // a face whose box is farther than R or than the voxel's best cannot matter
-                                if (fb[0] > fb[3] || d2 >= SDF_R2 || d2 >= __uint_as_float(s.best[v])) continue;
+                                const uint2 fb = s.fbox[slot];
+                                int qx, qy, qz;
+                                voxel_q8(s.worklist[v], qx, qy, qz);
+                                const int d2 = qbox_d2(fb, qx, qy, qz);
+                                if (!(fb.x >> 24) || (SDF_SHELL ? (d2 < t_lo || d2 >= t_hi) : d2 >= SDF_R2_Q8) || (float)d2 * Q8_TO_D2 >= __uint_as_float(s.best[v])) continue;
                                 const uint32_t pos = atomicAdd(qn, 1u);
                                 if (pos < Q_CAP) s.queue[pos] = ((uint32_t)v << 16) | (uint32_t)slot;
                                 else pair_test(s, cl_tri, v, slot);          // queue full: test in place
                             }
                             __syncthreads();
-                            // (C) exact tests
                             const int nq = min((int)*qn, Q_CAP);
                             if (tid == 0) s.qn[qb ^ 1] = 0u;              // last read before this round's (B)
                             if (a.stats && tid == 0) { a.stats[b * 32 + 7] += (int)*qn; a.stats[b * 32 + 23 + 2 * band] += (int)*qn; }
@@ -745,6 +786,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
 
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     if (B <= 0) return IHMR_OK;
+    if (reinterpret_cast<uintptr_t>(a.verts) & 15u) { set_error("sdf: the vertex buffer must be 16-byte aligned"); return IHMR_E_INVALID; }
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_sdf, sizeof(SdfSmem), configured)) return rc;
     k_sdf<<<B, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, m->faces[0], m->faces[1],
