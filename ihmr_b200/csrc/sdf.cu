@@ -51,7 +51,10 @@ constexpr int PHI_CAP = 2048;
 constexpr int Q_CAP = 6144;
 constexpr int P_CAP = 3072;
 constexpr int V_CHUNK = 640;
-constexpr int P_CHUNK = 480;
+#ifndef SDF_P_CHUNK
+#define SDF_P_CHUNK 480
+#endif
+constexpr int P_CHUNK = SDF_P_CHUNK;
 #endif
 #ifndef SDF_R_CELLS
 #define SDF_R_CELLS 2.5f
@@ -60,6 +63,9 @@ constexpr int P_CHUNK = 480;
 // voxel centres are the integers 8i + 4, box distances are exact integers.
 #ifndef SDF_SHELL
 #define SDF_SHELL 0
+#endif
+#ifndef SDF_SPLIT
+#define SDF_SPLIT 2                  // minimum number of (B)/(C) rounds of the inner band
 #endif
 #ifndef SDF_T0
 #define SDF_T0 8                     // squared radius of round 0 in Q8 units (0.35 voxel)
@@ -665,11 +671,15 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                         __syncthreads();
                         const int np = min((int)*pn, P_CAP);
                         if (a.stats && tid == 0) { a.stats[b * 32 + 6] += (int)*pn; a.stats[b * 32 + 22 + 2 * band] += (int)*pn; }
-                        for (int p0 = 0; p0 < np; p0 += P_CHUNK, qb ^= 1) {
+                        // The pairs are dealt round-robin to the (B)/(C) rounds (at least SDF_SPLIT of them in the
+                        // inner band): a voxel's clusters land in different rounds, so all but the first see its
+                        // best distance and reject most faces.
+                        const int nround = max((np + P_CHUNK - 1) / P_CHUNK, band == 0 ? min(SDF_SPLIT, np) : 1);
+                        for (int r = 0; r < nround && np > 0; ++r, qb ^= 1) {
                             uint32_t* qn = &s.qn[qb];
-                            const int npc = min(P_CHUNK, np - p0);
+                            const int npc = (np - r + nround - 1) / nround;      // pairs r, r + nround, ...
                             for (int jj = tid; jj < npc * 32; jj += SDF_THREADS) {
-                                const uint32_t pr = s.pairs[p0 + (jj >> 5)];
+                                const uint32_t pr = s.pairs[r + (jj >> 5) * nround];
                                 const int v = pr >> 6, slot = (pr & 63u) * 32 + (jj & 31);
                                 const uint2 fb = s.fbox[slot];
                                 int qx, qy, qz;
