@@ -83,7 +83,7 @@ struct __align__(16) SdfSmem {
     float U[NV * 3];            // normalised grid-hand vertices
     uint32_t needed[G * G];     // marked voxels per (z,y) column
     uint32_t work[G * G];       // parity bits, then marked & inside
-    uint32_t row_mask[G];       // bit j of row k: column (k,j) holds a marked & inside voxel
+    int region[4];              // lattice bounds of the marked columns: y min, y max, z min, z max
     uint16_t coloff[G * G];     // exclusive prefix of popc(work)
     uint16_t worklist[PHI_CAP]; // (column << 5) | x of the voxels of the current pass
     uint16_t far_list[PHI_CAP]; // voxels whose nearest face is beyond SDF_R
@@ -304,6 +304,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
     // Both hands of the frame are staged once by the TMA engine (one 1-D bulk copy completing on an
     // mbarrier); every later phase reads them from shared memory.
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar);
+    float mask = 1.0f;                   // both-hands flag; loaded here so that its latency hides behind the staging
+    if (a.hand_type) mask = (a.hand_type[b * 2] + a.hand_type[b * 2 + 1] > 1.5f) ? 1.0f : 0.0f;
     if (tid == 0) {
         constexpr uint32_t V_BYTES = 2 * NV * 3 * sizeof(float);
         static_assert(V_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -381,8 +383,6 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
     }
     SDF_STAT(1)
 
-    float mask = 1.0f;
-    if (a.hand_type) mask = (a.hand_type[b * 2] + a.hand_type[b * 2 + 1] > 1.5f) ? 1.0f : 0.0f;
     float loss_part = 0.f;
 
     for (int h = 0; h < 2; ++h) {
@@ -410,9 +410,14 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
             wlo[c] = s.box[h][0][c] - scale * (2.2f / G);
             whi[c] = s.box[h][1][c] + scale * (2.2f / G);
         }
-        for (int i = tid; i < G * G; i += SDF_THREADS) { s.needed[i] = 0u; s.work[i] = 0u; }
-        if (tid < G) s.row_mask[tid] = 0u;
-        __syncthreads();
+        // block-uniform: can any query vertex pass the reject box at all?
+        const bool may = s.box[o][0][0] <= whi[0] && s.box[o][1][1] >= wlo[1] && s.box[o][0][1] <= whi[1] &&
+                         s.box[o][1][2] >= wlo[2] && s.box[o][0][2] <= whi[2];
+        if (may) {
+            for (int i = tid; i < G * G; i += SDF_THREADS) { s.needed[i] = 0u; s.work[i] = 0u; }
+            if (tid < 4) s.region[tid] = (tid & 1) ? -1 : G;
+            __syncthreads();
+        }
 
         // ---- query vertices: normalised position, voxel corners, mark
         // (the cell of a query vertex is recomputed at sampling time rather than kept in registers)
@@ -436,18 +441,19 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         float acc[SDF_SLOTS][4];
         uint32_t act = 0u;
         bool any = false;
+        int reg[4] = {G, -1, G, -1};         // this thread's marked columns: y min, y max, z min, z max
         float pq[SDF_SLOTS][3];              // all loads in flight before the first use
 #pragma unroll
         for (int sl = 0; sl < SDF_SLOTS; ++sl) {
             const int v = tid + sl * SDF_THREADS;
             pq[sl][0] = 3e30f; pq[sl][1] = 0.f; pq[sl][2] = 0.f;         // beyond whi[0]: rejected
-            if (v < NV) load_vert(o, v, pq[sl]);
+            if (may && v < NV) load_vert(o, v, pq[sl]);
         }
 #pragma unroll
         for (int sl = 0; sl < SDF_SLOTS; ++sl) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[sl][c] = 0.f;
-            {
+            if (may) {
                 float fr[3];
                 int i0[3];
                 const bool in = locate(pq[sl], fr, i0);
@@ -467,12 +473,28 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                             uint32_t bits = 0u;
                             if (i0[0] >= 0 && voxel_center(i0[0]) <= thi[0]) bits |= 1u << i0[0];
                             if (i0[0] + 1 < G && voxel_center(i0[0] + 1) <= thi[0]) bits |= 1u << (i0[0] + 1);
-                            if (bits) { any = true; atomicOr(&s.needed[zc * G + yc], bits); }
+                            if (bits) {
+                                any = true;
+                                atomicOr(&s.needed[zc * G + yc], bits);
+                                reg[0] = min(reg[0], yc); reg[1] = max(reg[1], yc); reg[2] = min(reg[2], zc); reg[3] = max(reg[3], zc);
+                            }
                         }
                 }
             }
         }
-        const bool any_block = __syncthreads_or(any);
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int r = reg[i];
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) {
+                    const int t = __shfl_xor_sync(0xffffffffu, r, sft);
+                    r = (i & 1) ? max(r, t) : min(r, t);
+                }
+                if (lane == 0) { if (i & 1) atomicMax(&s.region[i], r); else atomicMin(&s.region[i], r); }
+            }
+        }
+        const bool any_block = may && __syncthreads_or(any);
         if (a.stats) {
             int nact = 0;
             for (int sl = 0; sl < SDF_SLOTS; ++sl) nact += __syncthreads_count((act >> sl) & 1u);
@@ -507,6 +529,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 while (cnt > 0 && !(x > voxel_center(cnt - 1))) --cnt;
                 if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
             };
+            const float ry0 = voxel_center(s.region[0]) - 0.01f * (2.0f / G), ry1 = voxel_center(s.region[1]) + 0.01f * (2.0f / G);
+            const float rz0 = voxel_center(s.region[2]) - 0.01f * (2.0f / G), rz1 = voxel_center(s.region[3]) + 0.01f * (2.0f / G);
             for (int f0 = 0; f0 < NF; f0 += SDF_THREADS) {
                 const int f = f0 + tid;
                 int j0 = 0, j1 = -1, k0 = 0, k1 = -1;
@@ -515,11 +539,15 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
                     const float ymin = fminf(A_[1], fminf(B_[1], C_[1])), ymax = fmaxf(A_[1], fmaxf(B_[1], C_[1]));
                     const float zmin = fminf(A_[2], fminf(B_[2], C_[2])), zmax = fmaxf(A_[2], fmaxf(B_[2], C_[2]));
-                    // lattice points y_j = (2j+1-G)/G inside [ymin,ymax]
-                    // (1e-3 of a cell absorbs the rounding of the index arithmetic; the ray test itself decides)
-                    j0 = max(0, (int)ceilf((ymin * G + (G - 1)) * 0.5f - 1e-3f)); j1 = min(G - 1, (int)floorf((ymax * G + (G - 1)) * 0.5f + 1e-3f));
-                    k0 = max(0, (int)ceilf((zmin * G + (G - 1)) * 0.5f - 1e-3f)); k1 = min(G - 1, (int)floorf((zmax * G + (G - 1)) * 0.5f + 1e-3f));
+                    // faces that miss the (y,z) region of the marked columns (with 1/100 cell to spare) are done
+                    if (!(ymax < ry0 || ymin > ry1 || zmax < rz0 || zmin > rz1)) {
+                        // lattice points y_j = (2j+1-G)/G inside [ymin,ymax]
+                        // (1e-3 of a cell absorbs the rounding of the index arithmetic; the ray test itself decides)
+                        j0 = max(0, (int)ceilf((ymin * G + (G - 1)) * 0.5f - 1e-3f)); j1 = min(G - 1, (int)floorf((ymax * G + (G - 1)) * 0.5f + 1e-3f));
+                        k0 = max(0, (int)ceilf((zmin * G + (G - 1)) * 0.5f - 1e-3f)); k1 = min(G - 1, (int)floorf((zmax * G + (G - 1)) * 0.5f + 1e-3f));
+                    }
                 }
+                if (__ballot_sync(0xffffffffu, j1 >= j0 && k1 >= k0) == 0u) continue;      // no lane covers a lattice point
                 // Most faces cover at most 2 x 2 lattice points: those are handled with the warp converged and
                 // one queue reservation per warp and lattice slot; the lattice box of a larger face is spread
                 // over the lanes of its warp.
@@ -574,7 +602,6 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 const uint32_t wk = s.needed[c] & s.work[c];
                 s.work[c] = wk;
                 cnt[i] = __popc(wk);
-                if (wk) atomicOr(&s.row_mask[c >> 5], 1u << (c & 31));
             }
             if (a.stats) {
                 int nm = 0;
