@@ -85,7 +85,7 @@ struct __align__(16) SdfSmem {
     uint32_t work[G * G];       // parity bits, then marked & inside
     int region[4];              // lattice bounds of the marked columns: y min, y max, z min, z max
     uint16_t coloff[G * G];     // exclusive prefix of popc(work)
-    uint16_t worklist[PHI_CAP]; // (column << 5) | x of the voxels of the current pass
+    uint32_t worklist[PHI_CAP]; // voxels of the current pass as packed Q8 centres: 8x+4 | (8y+4) << 8 | (8z+4) << 16
     uint16_t far_list[PHI_CAP]; // voxels whose nearest face is beyond SDF_R
     uint32_t best[PHI_CAP];     // bit pattern of the best squared distance (>= 0: orders like uint); then phi
     uint32_t queue[Q_CAP];      // (voxel index << 16) | slot of the face in the cluster table
@@ -222,20 +222,26 @@ __device__ __forceinline__ int block_scan_1024(const int (&cnt)[SDF_CPT], int (&
     return total;
 }
 
-// squared distance, in Q8 units, from the voxel centre (qx,qy,qz) to a packed box
-__device__ __forceinline__ int qbox_d2(uint2 bx, int qx, int qy, int qz) {
-    const int lx = bx.x & 255, ly = (bx.x >> 8) & 255, lz = (bx.x >> 16) & 255;
-    const int hx = bx.y & 255, hy = (bx.y >> 8) & 255, hz = (bx.y >> 16) & 255;
-    const int dx = max(max(lx - qx, qx - hx), 0), dy = max(max(ly - qy, qy - hy), 0), dz = max(max(lz - qz, qz - hz), 0);
-    return dx * dx + dy * dy + dz * dz;
+// Four times the squared distance, in Q8 units, from a packed voxel centre to a packed box, with byte-wise
+// SIMD only: per axis 2 d = |q - lo| + |q - hi| - (hi - lo), and the sum of squares is expanded into
+// dot products of the byte vectors (VABSDIFF4 + IDP.4A; no per-byte overflow).  Byte 3 is 0 in voxels and
+// in valid boxes; boxes of empty table slots carry 255 there, which puts them beyond every radius.
+__device__ __forceinline__ int qbox_4d2(uint2 bx, uint32_t q) {
+    const uint32_t a = __vabsdiffu4(q, bx.x), b = __vabsdiffu4(q, bx.y), w = __vabsdiffu4(bx.y, bx.x);
+    const uint32_t sq = __dp4a(w, w, __dp4a(b, b, __dp4a(a, a, 0u)));
+    const uint32_t cr = __dp4a(b, w, __dp4a(a, w, 0u));
+    return (int)(sq + 2u * (__dp4a(a, b, 0u) - cr));
 }
 
-__device__ __forceinline__ void voxel_q8(int code, int& qx, int& qy, int& qz) {
-    qx = ((code << 3) & 0xf8) | 4; qy = ((code >> 2) & 0xf8) | 4; qz = ((code >> 7) & 0xf8) | 4;
+__device__ __forceinline__ uint32_t pack_q8(int x, int y, int z) {
+    return (uint32_t)(8 * x + 4) | ((uint32_t)(8 * y + 4) << 8) | ((uint32_t)(8 * z + 4) << 16);
 }
 
-__device__ __forceinline__ void voxel_pos(int code, float* q) {
-    q[0] = voxel_center(code & 31); q[1] = voxel_center((code >> 5) & 31); q[2] = voxel_center(code >> 10);
+// voxel centre (2i + 1 - G) / G = (8i + 4) / 128 - 1, exact either way
+__device__ __forceinline__ void voxel_pos(uint32_t q8, float* q) {
+    q[0] = fmaf((float)(q8 & 255u), 1.0f / 128.0f, -1.0f);
+    q[1] = fmaf((float)((q8 >> 8) & 255u), 1.0f / 128.0f, -1.0f);
+    q[2] = fmaf((float)((q8 >> 16) & 255u), 1.0f / 128.0f, -1.0f);
 }
 
 // one exact (voxel, face) test; the result lowers the voxel's best squared distance
@@ -252,18 +258,16 @@ __device__ __forceinline__ void pair_test(SdfSmem& s, const ushort4* __restrict_
 // box first, one face per lane, until the nearest unvisited box is farther than the best
 // distance.  The open wrist makes some far-away voxels "inside" (odd crossing parity), and the
 // reference's brute-force loop gives them their true distance, so they must be exact too.
-__device__ __forceinline__ float eval_voxel_far(const SdfSmem& s, const ushort4* __restrict__ cl_tri, int code,
+__device__ __forceinline__ float eval_voxel_far(const SdfSmem& s, const ushort4* __restrict__ cl_tri, uint32_t q8,
                                                 float best, int lane) {
     float q[3];
-    voxel_pos(code, q);
-    int qx, qy, qz;
-    voxel_q8(code, qx, qy, qz);
+    voxel_pos(q8, q);
     float lb[2];                         // lower bounds: the quantised boxes contain the true ones
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         const int c = lane + 32 * t;
         lb[t] = 1e30f;
-        if (c < NCL) lb[t] = (float)qbox_d2(s.cl_box[c], qx, qy, qz) * Q8_TO_D2;
+        if (c < NCL) lb[t] = (float)qbox_4d2(s.cl_box[c], q8) * (0.25f * Q8_TO_D2);
     }
     for (int it = 0; it < NCL; ++it) {
         float m = fminf(lb[0], lb[1]);
@@ -627,7 +631,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                     while (wk) {
                         const int x = __ffs(wk) - 1;
                         wk &= wk - 1;
-                        if (idx >= pass0 && idx < pass1) s.worklist[idx - pass0] = (uint16_t)((c << 5) | x);
+                        if (idx >= pass0 && idx < pass1) s.worklist[idx - pass0] = pack_q8(x, c & 31, c >> 5);
                         ++idx;
                     }
                 }
@@ -650,8 +654,10 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                             hi[ax] = max(0, min(255, (int)ceilf((hgh + 1.0f) * 128.0f + 1e-3f)));
                         }
                     }
-                    s.fbox[c * 32 + lane] = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16) | (id.w ? 1u << 24 : 0u),
-                                                       (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16));
+                    const uint32_t far = id.w ? 0u : 255u << 24;        // empty slot: beyond every radius
+                    s.fbox[c * 32 + lane] = id.w ? make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16),
+                                                              (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16))
+                                                 : make_uint2(far, far);
 #pragma unroll
                     for (int ax = 0; ax < 3; ++ax) {
 #pragma unroll
@@ -661,7 +667,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                         }
                     }
                     if (lane == 0)
-                        s.cl_box[c] = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16) | (1u << 24),
+                        s.cl_box[c] = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16),
                                                  (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16));
                 }
                 __syncthreads();
@@ -687,10 +693,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                             const int vl = i / NCL, c = i - vl * NCL, v = v0 + vl;
                             const float bv = __uint_as_float(s.best[v]);
                             if (bv < b_lo) continue;
-                            int qx, qy, qz;
-                            voxel_q8(s.worklist[v], qx, qy, qz);
-                            const int d2 = qbox_d2(s.cl_box[c], qx, qy, qz);
-                            if ((!SDF_SHELL && d2 < t_lo) || d2 >= t_hi || (float)d2 * Q8_TO_D2 >= bv) continue;
+                            const int d2 = qbox_4d2(s.cl_box[c], s.worklist[v]);          // 4 x squared distance
+                            if ((!SDF_SHELL && d2 < 4 * t_lo) || d2 >= 4 * t_hi || (float)d2 * (0.25f * Q8_TO_D2) >= bv) continue;
                             const uint32_t pos = atomicAdd(pn, 1u);
                             if (pos < P_CAP) s.pairs[pos] = ((uint32_t)v << 6) | (uint32_t)c;
                             else for (int l = 0; l < 32; ++l) if (cl_tri[c * 32 + l].w) pair_test(s, cl_tri, v, c * 32 + l);
@@ -709,10 +713,8 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                                 const uint32_t pr = s.pairs[r + (jj >> 5) * nround];
                                 const int v = pr >> 6, slot = (pr & 63u) * 32 + (jj & 31);
                                 const uint2 fb = s.fbox[slot];
-                                int qx, qy, qz;
-                                voxel_q8(s.worklist[v], qx, qy, qz);
-                                const int d2 = qbox_d2(fb, qx, qy, qz);
-                                if (!(fb.x >> 24) || (SDF_SHELL ? (d2 < t_lo || d2 >= t_hi) : d2 >= SDF_R2_Q8) || (float)d2 * Q8_TO_D2 >= __uint_as_float(s.best[v])) continue;
+                                const int d2 = qbox_4d2(fb, s.worklist[v]);                   // 4 x squared distance
+                                if ((SDF_SHELL ? (d2 < 4 * t_lo || d2 >= 4 * t_hi) : d2 >= 4 * SDF_R2_Q8) || (float)d2 * (0.25f * Q8_TO_D2) >= __uint_as_float(s.best[v])) continue;
                                 const uint32_t pos = atomicAdd(qn, 1u);
                                 if (pos < Q_CAP) s.queue[pos] = ((uint32_t)v << 16) | (uint32_t)slot;
                                 else pair_test(s, cl_tri, v, slot);          // queue full: test in place

@@ -15,12 +15,13 @@ for r in rows[start + 1:]:
     if r and r[0] in ("File Path", "Line No"):
         break
     if r and r[0].isdigit() and r[ci].replace(".", "").isdigit():
-        lines.append((int(r[0]), int(r[ci]), int(r[li]), int(r[ti]), r[1]))
+        num = lambda x: int(x) if x.replace('.', '').isdigit() else 0
+        lines.append((int(r[0]), num(r[ci]), num(r[li]), num(r[ti]), r[1]))
 tot = sum(l[1] for l in lines); tots = sum(l[2] for l in lines)
 print(f"total warp-inst {tot:.3e}, samples {tots}")
 src = open(srcpath).read().split("\n")
 marks = [(i + 1, t.strip()[:80]) for i, t in enumerate(src)
-         if t.strip().startswith("// ----") or t.strip().startswith("// (") or re.match(r"^(__device__|__global__|template|static|int launch)", t)]
+         if t.strip().startswith("// ----") or t.strip().startswith("// (") or t.strip().startswith("//@") or re.match(r"^(__device__|__global__|template|static|int launch)", t)]
 marks.append((10 ** 9, "end"))
 for (a, name), (b, _) in zip(marks[:-1], marks[1:]):
     sel = [l for l in lines if a <= l[0] < b]
