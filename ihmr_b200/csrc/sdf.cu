@@ -95,6 +95,8 @@ struct __align__(16) SdfSmem {
                                 // .x = lo x | y << 8 | z << 16 | valid << 24, .y = hi x | y << 8 | z << 16
     float red[64];
     float box[2][2][3];         // [hand][lo/hi][xyz]
+    int boxi[2][2][3];          // the same as order-preserving integers while it is being reduced
+    float dirp[2][16];          // per grid hand: centre xyz, scale, tlo xyz, thi xyz, wlo xyz, whi xyz
     float shift[4];
     int scan_warp[SDF_WARPS];
     uint32_t qn[2];             // queue fill, double buffered by round
@@ -164,6 +166,10 @@ __device__ __forceinline__ float pt_tri_dist2(const float* p, const float* a, co
     const float din = dot3(e, e);
     return (va >= 0.f && vb >= 0.f && vc >= 0.f) ? fminf(best, din) : best;
 }
+
+// floats <-> integers with the same ordering (an involution on the bit pattern)
+__device__ __forceinline__ int float_ordered(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
 // ---- block primitives ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -308,6 +314,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
     // Both hands of the frame are staged once by the TMA engine (one 1-D bulk copy completing on an
     // mbarrier); every later phase reads them from shared memory.
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s.bar);
+    if (tid < 12) (&s.boxi[0][0][0])[tid] = ((tid / 3) & 1) ? (int)0x80000000 : 0x7fffffff;
     float mask = 1.0f;                   // both-hands flag; loaded here so that its latency hides behind the staging
     if (a.hand_type) mask = (a.hand_type[b * 2] + a.hand_type[b * 2 + 1] > 1.5f) ? 1.0f : 0.0f;
     if (tid == 0) {
@@ -363,25 +370,37 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 for (int c = 0; c < 3; ++c) { lo[hnd][c] = fminf(lo[hnd][c], p[c]); hi[hnd][c] = fmaxf(hi[hnd][c], p[c]); }
             }
         }
-        float* scratch = reinterpret_cast<float*>(s.queue);
+        // floats as order-preserving integers: one REDUX per value and warp, one shared atomic per warp
 #pragma unroll
         for (int hnd = 0; hnd < 2; ++hnd)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float l = lo[hnd][c], hgh = hi[hnd][c];
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) {
-                    l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
-                    hgh = fmaxf(hgh, __shfl_xor_sync(0xffffffffu, hgh, o));
-                }
-                if (lane == 0) { scratch[(hnd * 3 + c) * 2 * SDF_WARPS + warp] = l; scratch[(hnd * 3 + c) * 2 * SDF_WARPS + SDF_WARPS + warp] = hgh; }
+                const int l = __reduce_min_sync(0xffffffffu, float_ordered(lo[hnd][c]));
+                const int hgh = __reduce_max_sync(0xffffffffu, float_ordered(hi[hnd][c]));
+                if (lane == 0) { atomicMin(&s.boxi[hnd][0][c], l); atomicMax(&s.boxi[hnd][1][c], hgh); }
             }
         __syncthreads();
-        if (tid < 6) {
-            float l = 1e30f, hgh = -1e30f;
-            for (int w = 0; w < SDF_WARPS; ++w) { l = fminf(l, scratch[tid * 2 * SDF_WARPS + w]); hgh = fmaxf(hgh, scratch[tid * 2 * SDF_WARPS + SDF_WARPS + w]); }
-            s.box[tid / 3][0][tid % 3] = l;
-            s.box[tid / 3][1][tid % 3] = hgh;
+        // one thread per hand derives what both directions need (Appendix B: centre, scale = 0.6 * max extent)
+        if (tid < 2) {
+            float blo[3], bhi[3], cen[3], ext = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                blo[c] = ordered_float(s.boxi[tid][0][c]); bhi[c] = ordered_float(s.boxi[tid][1][c]);
+                s.box[tid][0][c] = blo[c]; s.box[tid][1][c] = bhi[c];
+                cen[c] = (blo[c] + bhi[c]) * 0.5f;
+                ext = fmaxf(ext, bhi[c] - blo[c]);
+            }
+            const float scale = 0.6f * ext;      // (1 + 0.2) * 0.5 * max extent
+            float* d = s.dirp[tid];
+            d[3] = scale;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                d[c] = cen[c];
+                d[4 + c] = (blo[c] - cen[c]) / scale - 1e-4f;      // normalised extent of the hand itself (+ rounding slack)
+                d[7 + c] = (bhi[c] - cen[c]) / scale + 1e-4f;
+                d[10 + c] = blo[c] - scale * (2.2f / G);           // the same box in world units, grown by one voxel (+ slack)
+                d[13 + c] = bhi[c] + scale * (2.2f / G);
+            }
         }
         __syncthreads();
     }
@@ -394,25 +413,12 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         const int o = 1 - h;
         const ushort4* f4 = reinterpret_cast<const ushort4*>(h ? faces_l : faces_r);
         const ushort4* cl_tri = h ? cl_l : cl_r;
-        float cen[3], ext = 0.f;
+        float cen[3], tlo[3], thi[3], wlo[3], whi[3];
+        const float scale = s.dirp[h][3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            cen[c] = (s.box[h][0][c] + s.box[h][1][c]) * 0.5f;
-            ext = fmaxf(ext, s.box[h][1][c] - s.box[h][0][c]);
-        }
-        const float scale = 0.6f * ext;      // (1 + 0.2) * 0.5 * max extent
-        float tlo[3], thi[3];                // normalised extent of the grid hand itself (+ rounding slack)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            tlo[c] = (s.box[h][0][c] - cen[c]) / scale - 1e-4f;
-            thi[c] = (s.box[h][1][c] - cen[c]) / scale + 1e-4f;
-        }
-
-        float wlo[3], whi[3];                // the same box in world units, grown by one voxel (+ slack)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            wlo[c] = s.box[h][0][c] - scale * (2.2f / G);
-            whi[c] = s.box[h][1][c] + scale * (2.2f / G);
+            cen[c] = s.dirp[h][c]; tlo[c] = s.dirp[h][4 + c]; thi[c] = s.dirp[h][7 + c];
+            wlo[c] = s.dirp[h][10 + c]; whi[c] = s.dirp[h][13 + c];
         }
         // block-uniform: can any query vertex pass the reject box at all?
         const bool may = s.box[o][0][0] <= whi[0] && s.box[o][1][1] >= wlo[1] && s.box[o][0][1] <= whi[1] &&
