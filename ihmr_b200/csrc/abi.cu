@@ -54,6 +54,19 @@ static void build_shape_rows(const float* shapedirs, const float* Jreg, std::vec
             }
 }
 
+// shape directions per vertex as 8 planes of float4: entry e = c * 10 + k of vertex v sits at
+// Sv[((e / 4) * NV + v) * 4 + e % 4] (entries 30, 31 are padding)
+static std::vector<float> build_sv(const float* shapedirs) {
+    std::vector<float> sv((size_t)NV * 32, 0.f);
+    for (int v = 0; v < NV; ++v)
+        for (int c = 0; c < 3; ++c)
+            for (int k = 0; k < NB; ++k) {
+                const int e = c * NB + k;
+                sv[((size_t)(e / 4) * NV + v) * 4 + e % 4] = shapedirs[((size_t)v * 3 + c) * NB + k];
+            }
+    return sv;
+}
+
 // Static spatial clustering of the faces (rest pose): recursive median split along the longest
 // axis of the centroids into ceil(NF/32) groups of <= 32 faces.  The posed mesh is articulated,
 // so rest-pose neighbours stay neighbours and the per-frame cluster boxes stay tight.
@@ -183,6 +196,7 @@ int ihmr_model_create(const float* v_template, const float* shapedirs, const flo
     if ((rc = upload(&m->D, D)) || (rc = upload(&m->DT, DT)) || (rc = upload(&m->vtemp, vt)) ||
         (rc = upload(&m->Jt, Jt)) || (rc = upload(&m->Js, Js)) || (rc = upload(&m->Wt, Wt)) ||
         (rc = upload(&m->W4, W4)) || (rc = upload(&m->hands_mean, hm)) || (rc = upload(&m->Jreg, Jreg)) ||
+        (rc = upload(&m->Sv, build_sv(shapedirs))) ||
         (rc = upload(&m->faces[0], fr)) || (rc = upload(&m->faces[1], fl)) ||
         (rc = upload(&m->cl_tri[0], cluster_table(v_template, faces_right))) ||
         (rc = upload(&m->cl_tri[1], cluster_table(v_template, faces_left)))) {
@@ -197,7 +211,7 @@ void ihmr_model_destroy(ihmr_model_t* m) {
     if (!m) return;
     DeviceGuard guard(m->device);
     cudaFree(m->D); cudaFree(m->DT); cudaFree(m->vtemp); cudaFree(m->Jt); cudaFree(m->Js);
-    cudaFree(m->Wt); cudaFree(m->W4); cudaFree(m->hands_mean); cudaFree(m->Jreg);
+    cudaFree(m->Wt); cudaFree(m->W4); cudaFree(m->hands_mean); cudaFree(m->Jreg); cudaFree(m->Sv);
     cudaFree(m->faces[0]); cudaFree(m->faces[1]); cudaFree(m->cl_tri[0]); cudaFree(m->cl_tri[1]);
     delete m;
 }
@@ -215,6 +229,8 @@ int ihmr_model_update_shapedirs(ihmr_model_t* m, const float* shapedirs, ihmr_st
     IHMR_CUDA_OK(cudaMemcpyAsync(m->D, D.data(), D.size() * 4, cudaMemcpyHostToDevice, st));
     IHMR_CUDA_OK(cudaMemcpyAsync(m->DT, DT.data(), DT.size() * 4, cudaMemcpyHostToDevice, st));
     IHMR_CUDA_OK(cudaMemcpyAsync(m->Js, Js.data(), Js.size() * 4, cudaMemcpyHostToDevice, st));
+    const std::vector<float> sv = build_sv(shapedirs);
+    IHMR_CUDA_OK(cudaMemcpyAsync(m->Sv, sv.data(), sv.size() * 4, cudaMemcpyHostToDevice, st));
     IHMR_CUDA_OK(cudaStreamSynchronize(st));
     return IHMR_OK;
 }

@@ -76,6 +76,7 @@ struct ihmr_model {
     float* W4;       // (4, 778, 4) lbs weights, tiles of 4 joints: W4[t][v][i] = W[v][4t+i]
     float* hands_mean;  // (48) [0,0,0, hands_mean(45)]
     float* Jreg;     // (16, 778)  kept for update_shapedirs
+    float* Sv;       // (8, 778, 4) shapedirs per vertex, 8 float4 planes: entry c*10+k (30 used) (shape-only stages)
     uint16_t* faces[2];  // (1538, 4) u16 per hand (right, left), 4th lane unused
     uint16_t* cl_tri[2]; // (49 clusters x 32, 4) u16: vertex ids of the faces of each spatial cluster, lane 3 = valid
     int parents[16];

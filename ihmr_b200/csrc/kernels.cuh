@@ -49,6 +49,11 @@ int launch_rigid_prep(int n, HandSrc src, float* verts, float* joints, float* Lv
 int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
 int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips, const float* gjoints, const float* Lv,
                      const float* Lj, float* params_grad, cudaStream_t st);
+// shape-only stages (fused layout only): cache (T_v | T_v c_v) per vertex, then the affine forward / backward in beta
+int launch_shape_prep(const ihmr_model* m, int n, HandSrc src, const float* off, const float* A, float* cache, cudaStream_t st);
+int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st);
+int launch_shape_bwd(const ihmr_model* m, int n, const float* cache, const float* gverts, const float* gtips, float* dA,
+                     float* dX, cudaStream_t st);
 // C[M,Nc] = A[M,K] . B[Nc,K]^T on tcgen05 with 3xTF32 splitting (blend_tc.cu)
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                        cudaStream_t st);

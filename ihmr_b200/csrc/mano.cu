@@ -729,6 +729,350 @@ int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips
     return IHMR_OK;
 }
 
+// ------------------------------------------------------------------ shape-only path
+// When a stage updates nothing but the shape coefficients (opt_default stage 3,
+// /root/reference/src/strategies/opt_default.py:61-78) the rotations of the kinematic chain are fixed and the
+// layer is affine in beta:
+//     verts_v = T_v (c_v + S_v beta) + sum_j W[v,j] a_j(beta),
+// T_v = sum_j W[v,j] Rg_j (3x3) and c_v = v_template + pose offsets fixed for the stage, a_j = the
+// translation column of the joint transform A_j, which k_pose_prep recomputes every iteration together
+// with the joints.  The stage's first iteration runs the generic layer and k_shape_prep caches
+// (T_v | T_v c_v) as three float4 per vertex (one plane per row, lanes read consecutive words); afterwards the forward is 87 FMA per vertex and the
+// backward produces exactly what k_pose_bwd needs for beta: the translation column of dA
+// (sum_v W[v,j] g_v) and the beta entries of dX (sum_v S_v^T T_v^T g_v).  Both kernels stream the cache
+// (37 KB per hand) and are HBM bound instead of FP32 bound.
+constexpr int SH_THREADS = 416;   // 13 warps, vertices tid and tid + 416
+constexpr int SH_HPC = 8;         // hands per CTA
+
+// Sv is stored as 8 planes of float4 per vertex (plane i = entries 4i..4i+3 of the vertex's 30 values
+// [c * 10 + k]), so that the lanes of a warp read consecutive 16-byte words
+__device__ __forceinline__ void load_shape_row(const float* __restrict__ Sv, int v, float (&sv)[32]) {
+    const float4* p = reinterpret_cast<const float4*>(Sv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = p[i * NV + v];
+        sv[i * 4 + 0] = t.x; sv[i * 4 + 1] = t.y; sv[i * 4 + 2] = t.z; sv[i * 4 + 3] = t.w;
+    }
+}
+
+__device__ __forceinline__ void stage_hands(int n, int h0, int nh, const HandSrc& src, const float* __restrict__ A,
+                                            const float* __restrict__ W4, float4* sW4, float4 (*sA)[48], float (*sBeta)[12]) {
+    const int tid = threadIdx.x;
+    if (sW4) {
+        const float4* w = reinterpret_cast<const float4*>(W4);
+        for (int i = tid; i < 4 * NV; i += SH_THREADS) sW4[i] = w[i];
+    }
+    const float4* A4 = reinterpret_cast<const float4*>(A) + (size_t)h0 * 48;
+    for (int i = tid; i < nh * 48; i += SH_THREADS) sA[i / 48][i % 48] = A4[i];
+    for (int i = tid; i < nh * NB; i += SH_THREADS) {
+        const int h = h0 + i / NB, k = i % NB;
+        sBeta[i / NB][k] = src.params[(size_t)(h >> 1) * PD + P_SHAPE + NB * (h & 1) + k];
+    }
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+k_shape_prep(int n, HandSrc src, const float* __restrict__ off, const float* __restrict__ A,
+             const float* __restrict__ vtemp, const float* __restrict__ W4, const float* __restrict__ Sv,
+             float4* __restrict__ cache) {
+    extern __shared__ float4 smem4[];
+    float4* sW4 = smem4;                                                   // [4][778]
+    float4 (*sA)[48] = reinterpret_cast<float4 (*)[48]>(sW4 + 4 * NV);       // [SH_HPC][48]
+    float (*sBeta)[12] = reinterpret_cast<float (*)[12]>(sA + SH_HPC);       // [SH_HPC][12]
+    const int tid = threadIdx.x;
+    const int h0 = blockIdx.x * SH_HPC, nh = min(SH_HPC, n - h0);
+    stage_hands(n, h0, nh, src, A, W4, sW4, sA, sBeta);
+    __syncthreads();
+    for (int v = tid; v < NV; v += SH_THREADS) {
+        float sv[32];
+        load_shape_row(Sv, v, sv);
+        float w[NJ];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const float4 q = sW4[t * NV + v]; w[t * 4] = q.x; w[t * 4 + 1] = q.y; w[t * 4 + 2] = q.z; w[t * 4 + 3] = q.w; }
+        const float vt[3] = {vtemp[v * 3], vtemp[v * 3 + 1], vtemp[v * 3 + 2]};
+        for (int hh = 0; hh < nh; ++hh) {
+            const size_t h = h0 + hh;
+            float T[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) T[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float4 r0 = sA[hh][j * 3], r1 = sA[hh][j * 3 + 1], r2 = sA[hh][j * 3 + 2];
+                T[0] += w[j] * r0.x; T[1] += w[j] * r0.y; T[2] += w[j] * r0.z;
+                T[3] += w[j] * r1.x; T[4] += w[j] * r1.y; T[5] += w[j] * r1.z;
+                T[6] += w[j] * r2.x; T[7] += w[j] * r2.y; T[8] += w[j] * r2.z;
+            }
+            float c[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float sb = 0.f;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) sb += sv[a * NB + k] * sBeta[hh][k];
+                c[a] = vt[a] + (off[h * LDN + v * 3 + a] - sb);        // v_template + pose offsets only
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                cache[(h * 3 + r) * NV + v] = make_float4(T[r * 3], T[r * 3 + 1], T[r * 3 + 2],
+                                                          T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SH_THREADS, 2)
+k_shape_fwd(int n, HandSrc src, const float* __restrict__ A, const float* __restrict__ W4,
+            const float* __restrict__ Sv, const float4* __restrict__ cache, float* __restrict__ verts) {
+    extern __shared__ float4 smem4[];
+    float4* sW4 = smem4;
+    float4 (*sA)[48] = reinterpret_cast<float4 (*)[48]>(sW4 + 4 * NV);
+    float (*sBeta)[12] = reinterpret_cast<float (*)[12]>(sA + SH_HPC);
+    __shared__ float4 sT[SH_HPC][NJ];                       // translation columns a_j of this CTA's hands
+    const int tid = threadIdx.x;
+    const int h0 = blockIdx.x * SH_HPC, nh = min(SH_HPC, n - h0);
+    stage_hands(n, h0, nh, src, A, W4, sW4, sA, sBeta);
+    __syncthreads();
+    for (int i = tid; i < nh * NJ; i += SH_THREADS) {
+        const int hh = i / NJ, j = i % NJ;
+        sT[hh][j] = make_float4(sA[hh][j * 3].w, sA[hh][j * 3 + 1].w, sA[hh][j * 3 + 2].w, 0.f);
+    }
+    __syncthreads();
+    for (int v = tid; v < NV; v += SH_THREADS) {
+        float sv[32];
+        load_shape_row(Sv, v, sv);
+        float4 row[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) row[r] = cache[((size_t)h0 * 3 + r) * NV + v];
+        for (int hh = 0; hh < nh; ++hh) {
+            const size_t h = h0 + hh;
+            float4 nxt[3];                                   // the next hand's rows fly while this one is computed
+            if (hh + 1 < nh) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) nxt[r] = cache[((h + 1) * 3 + r) * NV + v];
+            }
+            const float4* b4 = reinterpret_cast<const float4*>(sBeta[hh]);
+            const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2];
+            const float beta[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+            float u[3], t[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float sb = 0.f;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) sb += sv[a * NB + k] * beta[k];
+                u[a] = sb;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w4 = sW4[q * NV + v];
+                const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 a = sT[hh][q * 4 + i];
+                    t[0] += wj[i] * a.x; t[1] += wj[i] * a.y; t[2] += wj[i] * a.z;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                verts[(h * NV + v) * 3 + r] = (row[r].w + t[r]) + (row[r].x * u[0] + row[r].y * u[1] + row[r].z * u[2]);
+            if (hh + 1 < nh) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) row[r] = nxt[r];
+            }
+        }
+    }
+}
+
+// reduce-scatter of 16 per-lane partial sums (fixed order): afterwards acc[0] of every lane holds the warp
+// total of element 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of the lane id)
+__device__ __forceinline__ void warp_reduce_scatter_16(float (&acc)[16], int lane) {
+#define IHMR_RS_STAGE(OFF, HALF)                                              \
+    {                                                                         \
+        const bool up = (lane & OFF) != 0;                                    \
+        _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                    \
+            float send = up ? acc[i] : acc[i + HALF];                         \
+            float keep = up ? acc[i + HALF] : acc[i];                         \
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);          \
+        }                                                                     \
+    }
+    IHMR_RS_STAGE(16, 8)
+    IHMR_RS_STAGE(8, 4)
+    IHMR_RS_STAGE(4, 2)
+    IHMR_RS_STAGE(2, 1)
+#undef IHMR_RS_STAGE
+    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+}
+
+constexpr int SH_WARPS = SH_THREADS / 32;
+constexpr int SH_ITEMS = 2;          // vertices per thread and hand (tid, tid + 416)
+
+// gradient of one vertex of one hand: g = gverts (+ fingertip part), optionally the cache rows
+struct ShapeItem {
+    float g[3];
+    float4 row[3];
+};
+
+template <bool ROWS>
+__device__ __forceinline__ void fetch_item(ShapeItem& it, size_t h, int v, const float* __restrict__ gverts,
+                                           const float* __restrict__ gtips, const float4* __restrict__ cache) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) it.g[c] = 0.f;
+    if (v >= NV) return;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) it.g[c] = gverts[(h * NV + v) * 3 + c];
+    if (gtips) {
+        const int tip = (v == 744) ? 0 : (v == 320) ? 1 : (v == 443) ? 2 : (v == 554) ? 3 : (v == 671) ? 4 : -1;
+        if (tip >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) it.g[c] += gtips[(h * 5 + tip) * 3 + c];
+        }
+    }
+    if (ROWS) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) it.row[r] = cache[(h * 3 + r) * NV + v];
+    }
+}
+
+// dA: translation column = sum_v W[v,j] g_v; the rotation block is written as zero (it only feeds the pose
+// gradients, which a shape-only stage does not use)
+__global__ void __launch_bounds__(SH_THREADS, 2)
+k_shape_bwd_t(int n, const float* __restrict__ W4, const float* __restrict__ gverts, const float* __restrict__ gtips,
+              float* __restrict__ dA) {
+    extern __shared__ float4 smem4[];
+    float4* sW4 = smem4;                                                    // [4][778]
+    float* sPart = reinterpret_cast<float*>(sW4 + 4 * NV);                   // [SH_WARPS][48]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h0 = blockIdx.x * SH_HPC, nh = min(SH_HPC, n - h0);
+    {
+        const float4* w = reinterpret_cast<const float4*>(W4);
+        for (int i = tid; i < 4 * NV; i += SH_THREADS) sW4[i] = w[i];
+    }
+    __syncthreads();
+    ShapeItem cur, nxt;
+    fetch_item<false>(cur, h0, tid, gverts, gtips, nullptr);
+    for (int hh = 0; hh < nh; ++hh) {
+        const size_t h = h0 + hh;
+        float acc[48];
+#pragma unroll
+        for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < SH_ITEMS; ++sl) {
+            const int v = tid + sl * SH_THREADS;
+            // next item: the other vertex of this hand, or the first vertex of the next hand
+            if (sl + 1 < SH_ITEMS) fetch_item<false>(nxt, h, v + SH_THREADS, gverts, gtips, nullptr);
+            else if (hh + 1 < nh) fetch_item<false>(nxt, h + 1, tid, gverts, gtips, nullptr);
+            if (v < NV) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float4 w4 = sW4[t * NV + v];
+                    const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) acc[(t * 4 + i) * 3 + r] += wj[i] * cur.g[r];
+                }
+            }
+            cur = nxt;
+        }
+        warp_reduce_scatter_48(acc, lane);
+        if ((lane & 1) == 0) {
+            const int seg = ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + ((lane >> 1) & 1) * 3;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sPart[warp * 48 + seg + i] = acc[i];
+        }
+        __syncthreads();
+        if (tid < 192) {
+            float sum = 0.f;
+            if ((tid & 3) == 3) {
+                const int e = (tid / 12) * 3 + (tid % 12) / 4;
+#pragma unroll
+                for (int w = 0; w < SH_WARPS; ++w) sum += sPart[w * 48 + e];
+            }
+            dA[h * 192 + tid] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+// dX: beta entries = sum_v S_v^T T_v^T g_v (what the blend contraction's backward would deliver), the
+// pose-feature entries are written as zero
+__global__ void __launch_bounds__(SH_THREADS, 2)
+k_shape_bwd_b(int n, const float* __restrict__ Sv, const float4* __restrict__ cache, const float* __restrict__ gverts,
+              const float* __restrict__ gtips, float* __restrict__ dX) {
+    __shared__ float sPart[SH_WARPS][16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h0 = blockIdx.x * SH_HPC, nh = min(SH_HPC, n - h0);
+    ShapeItem cur, nxt;
+    fetch_item<true>(cur, h0, tid, gverts, gtips, cache);
+    for (int hh = 0; hh < nh; ++hh) {
+        const size_t h = h0 + hh;
+        float accb[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) accb[i] = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < SH_ITEMS; ++sl) {
+            const int v = tid + sl * SH_THREADS;
+            if (sl + 1 < SH_ITEMS) fetch_item<true>(nxt, h, v + SH_THREADS, gverts, gtips, cache);
+            else if (hh + 1 < nh) fetch_item<true>(nxt, h + 1, tid, gverts, gtips, cache);
+            if (v < NV) {
+                // q = T^T g, the gradient of the shaped (unposed) vertex
+                const float q[3] = {cur.row[0].x * cur.g[0] + cur.row[1].x * cur.g[1] + cur.row[2].x * cur.g[2],
+                                    cur.row[0].y * cur.g[0] + cur.row[1].y * cur.g[1] + cur.row[2].y * cur.g[2],
+                                    cur.row[0].z * cur.g[0] + cur.row[1].z * cur.g[1] + cur.row[2].z * cur.g[2]};
+                float sv[32];
+                load_shape_row(Sv, v, sv);
+#pragma unroll
+                for (int k = 0; k < NB; ++k) accb[k] += sv[k] * q[0] + sv[NB + k] * q[1] + sv[2 * NB + k] * q[2];
+            }
+            cur = nxt;
+        }
+        warp_reduce_scatter_16(accb, lane);
+        if ((lane & 1) == 0) sPart[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = accb[0];
+        __syncthreads();
+        if (tid < KP) {
+            float sum = 0.f;
+            if (tid >= NPF && tid < NPF + NB) {
+#pragma unroll
+                for (int w = 0; w < SH_WARPS; ++w) sum += sPart[w][tid - NPF];
+            }
+            dX[h * KP + tid] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+constexpr size_t SHAPE_SMEM = sizeof(float4) * (4 * NV + SH_HPC * 48) + sizeof(float) * SH_HPC * 12;
+constexpr size_t SHAPE_BWD_SMEM = sizeof(float4) * 4 * NV + sizeof(float) * SH_WARPS * 48;
+
+int launch_shape_prep(const ihmr_model* m, int n, HandSrc src, const float* off, const float* A, float* cache, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    static unsigned long long configured = 0ull;
+    if (int rc = ensure_dynamic_smem(k_shape_prep, SHAPE_SMEM, configured)) return rc;
+    k_shape_prep<<<(n + SH_HPC - 1) / SH_HPC, SH_THREADS, SHAPE_SMEM, st>>>(n, src, off, A, m->vtemp, m->W4, m->Sv,
+                                                                            reinterpret_cast<float4*>(cache));
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    static unsigned long long configured = 0ull;
+    if (int rc = ensure_dynamic_smem(k_shape_fwd, SHAPE_SMEM, configured)) return rc;
+    k_shape_fwd<<<(n + SH_HPC - 1) / SH_HPC, SH_THREADS, SHAPE_SMEM, st>>>(n, src, A, m->W4, m->Sv,
+                                                                           reinterpret_cast<const float4*>(cache), verts);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
+int launch_shape_bwd(const ihmr_model* m, int n, const float* cache, const float* gverts, const float* gtips, float* dA,
+                     float* dX, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    static unsigned long long configured = 0ull;
+    if (int rc = ensure_dynamic_smem(k_shape_bwd_t, SHAPE_BWD_SMEM, configured)) return rc;
+    const int grid = (n + SH_HPC - 1) / SH_HPC;
+    k_shape_bwd_t<<<grid, SH_THREADS, SHAPE_BWD_SMEM, st>>>(n, m->W4, gverts, gtips, dA);
+    IHMR_LAUNCH_OK();
+    k_shape_bwd_b<<<grid, SH_THREADS, 0, st>>>(n, m->Sv, reinterpret_cast<const float4*>(cache), gverts, gtips, dX);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
 // -------------------------------------------------------------------------------- launchers
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -361,6 +361,7 @@ struct OptWs {
     ManoWs mano;
     float *verts, *gverts, *joints, *gjoints, *gtips, *grad, *m, *v, *best_params;
     float *col_loss, *gshift, *origin, *best, *j2d_b, *j3d_b, *loss_parts;
+    float* shape_cache;       // (N, 778, 3) float4: (T_v | T_v c_v) of the shape-only stages
     int* take;
 };
 
@@ -396,6 +397,7 @@ static size_t opt_ws_layout(void* base, int B, OptWs* out) {
     w.j3d_b = (float*)take((size_t)B * 4);
     w.loss_parts = (float*)take((size_t)B * 6 * 4);
     w.take = (int*)take((size_t)B * 4);
+    w.shape_cache = (float*)take((size_t)n * NV * 12 * 4);
     if (out) *out = w;
     return used;
 }
@@ -454,6 +456,8 @@ struct IterPlan {
                               // carry no gradient, their loss part is needed at snapshots only
     int rigid = 0;            // orientation-only stage: 1 = first iteration (generic forward, then cache the
                               // root-local geometry), 2 = later iterations (x = R0 L + J0); backward is rigid in both
+    int shape = 0;            // shape-only stage: 1 = first iteration (generic forward, then cache T_v | T_v c_v),
+                              // 2 = later iterations (affine in beta); backward is the affine one in both
 };
 
 static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
@@ -465,6 +469,12 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
     p.mano_bwd = live_mano;
     p.blend_bwd = live_blend;
     p.sdf_skip_grid = (!live_mano && !snapshot) ? 2 : 0;
+    if ((mask & (IHMR_P_R_SHAPE | IHMR_P_L_SHAPE)) &&
+        !(mask & (IHMR_P_R_POSE | IHMR_P_L_POSE | IHMR_P_R_ORIENT | IHMR_P_L_ORIENT))) {   // opt_default stage 3
+        p.shape = first ? 1 : 2;
+        p.blend_fwd = first;
+        p.blend_bwd = false;
+    }
     if (live_mano && !live_blend) {          // only the global orientations move (opt_default stage 1)
         p.rigid = first ? 1 : 2;
         p.mano_fwd = first;
@@ -485,7 +495,10 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     IHMR_TICK(prof, 1);
     if (plan.blend_fwd && (rc = launch_blend_fwd(m, 2 * B, w.mano.X, w.mano.off, st))) return rc;
     IHMR_TICK(prof, 2);
-    if (plan.mano_fwd && (rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st))) return rc;
+    if (plan.mano_fwd && plan.shape != 2 && (rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st))) return rc;
+    // shape-only stage: pose_prep above refreshed the joints and the translation columns of A
+    if (plan.shape == 1 && (rc = launch_shape_prep(m, 2 * B, src, w.mano.off, w.mano.A, w.shape_cache, st))) return rc;
+    if (plan.shape == 2 && (rc = launch_shape_fwd(m, 2 * B, src, w.mano.A, w.shape_cache, w.verts, st))) return rc;
     // orientation-only stage: the root-local geometry lives in the (otherwise idle) gposed / dA buffers
     if (plan.rigid == 1 && (rc = launch_rigid_prep(2 * B, src, w.verts, w.joints, w.mano.gposed, w.mano.dA, st))) return rc;
     if (plan.rigid == 2 && (rc = launch_rigid_fwd(2 * B, src, w.verts, w.joints, w.mano.gposed, w.mano.dA, st))) return rc;
@@ -503,14 +516,15 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     k_frame_loss<<<B, FL_THREADS, 0, st>>>(la);
     IHMR_LAUNCH_OK();
     IHMR_TICK(prof, 5);
-    if (plan.mano_bwd && (rc = launch_skin_bwd(m, 2 * B, w.mano.off, w.mano.A, w.gverts, w.gtips, w.mano.gposed, w.mano.dA, st))) return rc;
+    if (plan.mano_bwd && !plan.shape && (rc = launch_skin_bwd(m, 2 * B, w.mano.off, w.mano.A, w.gverts, w.gtips, w.mano.gposed, w.mano.dA, st))) return rc;
+    if (plan.shape && (rc = launch_shape_bwd(m, 2 * B, w.shape_cache, w.gverts, w.gtips, w.mano.dA, w.mano.dX, st))) return rc;
     IHMR_TICK(prof, 6);
     if (plan.blend_bwd && (rc = launch_blend_bwd(m, 2 * B, w.mano.gposed, w.mano.dX, st))) return rc;
     IHMR_TICK(prof, 7);
     if (plan.rigid && (rc = launch_rigid_bwd(2 * B, src, w.gverts, w.gtips, w.gjoints, w.mano.gposed, w.mano.dA, w.grad, st))) return rc;
     HandGrad hg;
     hg.params_grad = w.grad;
-    if (plan.mano_bwd && (rc = launch_pose_bwd(m, 2 * B, src, w.mano.dA, w.gjoints, plan.blend_bwd ? w.mano.dX : nullptr, hg, st))) return rc;
+    if (plan.mano_bwd && (rc = launch_pose_bwd(m, 2 * B, src, w.mano.dA, w.gjoints, (plan.blend_bwd || plan.shape) ? w.mano.dX : nullptr, hg, st))) return rc;
     IHMR_TICK(prof, 8);
     return IHMR_OK;
 }
