@@ -3,6 +3,8 @@
 // snapshot selection and the optimiser step.
 #include <math.h>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace ihmr {
@@ -469,6 +471,10 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
     p.mano_bwd = live_mano;
     p.blend_bwd = live_blend;
     p.sdf_skip_grid = (!live_mano && !snapshot) ? 2 : 0;
+    // IHMR_B200_GENERIC_STAGES=1 keeps every stage on the generic kernel chain (used by the tests that
+    // check the stage-specialised paths against it)
+    const char* generic = getenv("IHMR_B200_GENERIC_STAGES");
+    if (generic && generic[0] == '1') return p;
     if ((mask & (IHMR_P_R_SHAPE | IHMR_P_L_SHAPE)) &&
         !(mask & (IHMR_P_R_POSE | IHMR_P_L_POSE | IHMR_P_R_ORIENT | IHMR_P_L_ORIENT))) {   // opt_default stage 3
         p.shape = first ? 1 : 2;

@@ -250,6 +250,31 @@ def test_determinism_and_shard_invariance(model_root, oracle_layers):
         assert np.array_equal(np.concatenate([h[k] for h in halves]), full1[k]), k   # sharding bitwise
 
 
+def test_stage_shortcuts_match_generic_path(model_root, oracle_layers, monkeypatch):
+    """The orientation-only (rigid) and shape-only (affine) stage kernels are algebraic rewrites of the
+    generic chain: the same loop with IHMR_B200_GENERIC_STAGES=1 must agree to rounding."""
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default, with_epochs
+    B = 48
+    data = {k: np.concatenate([a, b]) for (k, a), (_, b) in zip(
+        H.make_batch(oracle_layers[0], 0, B // 2).items(), H.make_batch(oracle_layers[0], 512, B // 2, mode="collision").items())}
+    strat = with_epochs(opt_default, 6)
+
+    def run():
+        m = OptimizeModel(H.make_opt(model_root, B, save_mid_freq=2, strategy=strat, bs_norm=B))
+        m.set_input(H.torch_batch(data)); m.init_optimize(); m.optimize(0, 1)
+        return m.get_pred_result()
+
+    fast = run()
+    monkeypatch.setenv("IHMR_B200_GENERIC_STAGES", "1")
+    generic = run()
+    for k in ("pred_joints_3d", "pred_right_hand_verts", "pred_left_hand_verts"):
+        assert np.abs(fast[k] - generic[k]).max() <= 2e-5, k
+    for k in ("pred_pose_params", "pred_shape_params", "pred_hand_trans"):
+        assert np.abs(fast[k] - generic[k]).max() <= 2e-4, k
+    assert np.abs(fast["collision_loss"] - generic["collision_loss"]).max() <= 1e-4 * max(1.0, np.abs(generic["collision_loss"]).max())
+
+
 # ------------------------------------------------- less-travelled options of the reference
 def test_sgd_optimizer_matches_oracle_loop(model_root, oracle_layers):
     """opt.optimizer == 'sgd' (optimize_model.py:345-347): SGD with momentum 0.9."""
