@@ -67,6 +67,9 @@ constexpr int P_CHUNK = SDF_P_CHUNK;
 #ifndef SDF_SPLIT
 #define SDF_SPLIT 2                  // minimum number of (B)/(C) rounds of the inner band
 #endif
+#ifndef SDF_NBANDS
+#define SDF_NBANDS 2                 // measured: 2 bands (clusters containing the voxel, then everything within R) beat 1 and 3
+#endif
 #ifndef SDF_T0
 #define SDF_T0 8                     // squared radius of round 0 in Q8 units (0.35 voxel)
 #endif
@@ -686,9 +689,15 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 //   (B) thread per (pair, face of the cluster): face box in the shell [T_{k-1}, T_k) and closer
                 //       than the voxel's best -> (voxel, face) candidates (inner shells were done in earlier rounds)
                 //   (C) thread per candidate: exact point-triangle test, atomicMin into the voxel
+#if SDF_NBANDS == 3
                 const int t2[4] = {0, SDF_T0, SDF_T1, SDF_R2_Q8};
+#elif SDF_NBANDS == 2
+                const int t2[3] = {0, SDF_T0, SDF_R2_Q8};
+#else
+                const int t2[2] = {0, SDF_R2_Q8};
+#endif
                 int pa = 0, qb = 0;                  // fill counters of the current (A) / (B) round
-                for (int band = 0; band < 3; ++band) {
+                for (int band = 0; band < SDF_NBANDS; ++band) {
                     const int t_lo = t2[band], t_hi = t2[band + 1];
                     const float b_lo = (float)t_lo * Q8_TO_D2;
                     for (int v0 = 0; v0 < nvox; v0 += V_CHUNK, pa = (pa == 2) ? 0 : pa + 1) {

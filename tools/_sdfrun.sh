@@ -1,6 +1,2 @@
 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
-timeout 100 python tools/sdf_stats.py 2>&1 | grep -E "cycles|candidates:"
-B="python bench.py --frames 8192 --steps 2 --warmup 3 --no-cpu-baseline"
-P='import sys,json; d=json.loads(sys.stdin.read()); print(d["value"], d["ms_per_step"], [round(x["sdf"],3) for x in d["step_roofline"]["kernel_ms_per_stage"]])'
-timeout 200 $B 2>&1 | tail -1 | python -c "$P"
-for v in $VARIANTS; do echo $v; IHMR_B200_LIB=ihmr_b200/_lib/variants/libihmr_$v.so timeout 200 $B 2>&1 | tail -1 | python -c "$P"; done
+timeout 100 python tools/sdf_stats.py 2>&1 | grep -E "cycles per|candidates:|pairs:|candidates\+"
