@@ -429,6 +429,7 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         if (may) {
             for (int i = tid; i < G * G; i += SDF_THREADS) { s.needed[i] = 0u; s.work[i] = 0u; }
             if (tid < 4) s.region[tid] = (tid & 1) ? -1 : G;
+            if (tid == 0) s.qn[0] = 0u;                    // queue of the parity rasterisation
             __syncthreads();
         }
 
@@ -507,6 +508,15 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 if (lane == 0) { if (i & 1) atomicMax(&s.region[i], r); else atomicMin(&s.region[i], r); }
             }
         }
+        if (may) {
+            // ---- normalised grid-hand vertices (same phase as the marking: the barrier below covers both)
+            for (int v = tid; v < NV; v += SDF_THREADS) {
+                float p[3];
+                load_vert(h, v, p);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) s.U[v * 3 + c] = (p[c] - cen[c]) / scale;
+            }
+        }
         const bool any_block = may && __syncthreads_or(any);
         if (a.stats) {
             int nact = 0;
@@ -518,20 +528,10 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
         int total = 0;
 
         if (run) {
-            // ---- normalised grid-hand vertices
-            for (int v = tid; v < NV; v += SDF_THREADS) {
-                float p[3];
-                load_vert(h, v, p);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) s.U[v * 3 + c] = (p[c] - cen[c]) / scale;
-            }
-            __syncthreads();
             SDF_STAT(3)
             // ---- parity of the marked columns, two steps so that the ray tests run with full warps:
             //      (1) thread per face: lattice points inside its (y,z) box whose column is marked
             //          -> (face, column) items; (2) thread per item: the exact ray test
-            if (tid == 0) s.qn[0] = 0u;
-            __syncthreads();
             auto ray_item = [&](int f, int col) {
                 const ushort4 id = f4[f];
                 float x;
@@ -646,7 +646,6 @@ k_sdf(int B, SdfArgs a, const uint16_t* __restrict__ faces_r, const uint16_t* __
                 }
                 for (int i = tid; i < nvox; i += SDF_THREADS) s.best[i] = 0x7f7fffffu;
                 if (tid == 0) { s.qn[0] = 0u; s.qn[1] = 0u; s.pn[0] = 0u; s.pn[1] = 0u; s.pn[2] = 0u; s.far_count = 0; }
-                __syncthreads();
                 SDF_STAT(6)
                 // ---- nearest face of every voxel, bulk-synchronous and balanced (work is indexed by voxel)
                 //   (0) per face (static clusters of <= 32, spatially sorted): bounding box quantised outwards
