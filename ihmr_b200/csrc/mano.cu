@@ -742,7 +742,17 @@ int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips
 // (sum_v W[v,j] g_v) and the beta entries of dX (sum_v S_v^T T_v^T g_v).  Both kernels stream the cache
 // (37 KB per hand) and are HBM bound instead of FP32 bound.
 constexpr int SH_THREADS = 416;   // 13 warps, vertices tid and tid + 416
-constexpr int SH_HPC = 8;         // hands per CTA
+#ifndef SH_HPC_N
+#define SH_HPC_N 8
+#endif
+#ifndef SH_MINB_F
+#define SH_MINB_F 2
+#endif
+#ifndef SH_MINB_B
+#define SH_MINB_B 2
+#endif
+constexpr int SH_HPC = SH_HPC_N;  // hands per CTA
+constexpr int SH_ITEMS_F = 2;      // vertices per thread in k_shape_fwd
 
 // Sv is stored as 8 planes of float4 per vertex (plane i = entries 4i..4i+3 of the vertex's 30 values
 // [c * 10 + k]), so that the lanes of a warp read consecutive 16-byte words
@@ -817,65 +827,110 @@ k_shape_prep(int n, HandSrc src, const float* __restrict__ off, const float* __r
     }
 }
 
-__global__ void __launch_bounds__(SH_THREADS, 2)
+// The cache of a hand is one contiguous block (3 planes x 778 float4 = 37,344 B): it is streamed through a
+// ring of shared-memory stages by the TMA engine (one bulk copy per hand, mbarrier completion), three hands
+// ahead of the arithmetic, so the kernel runs at the speed of its loads with one CTA per SM.  Every thread
+// owns two vertices and keeps their skinning weights and shape directions in registers.
+constexpr int SHF_STAGES = 3;
+constexpr int SHF_HPC = 16;                                   // hands per CTA
+constexpr uint32_t SHAPE_CACHE_BYTES = 3 * NV * sizeof(float4);
+static_assert(SHAPE_CACHE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+__device__ __forceinline__ void shape_issue(const float4* cache, size_t h, float4* stage, unsigned long long* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(SHAPE_CACHE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(stage)), "l"(cache + h * 3 * NV), "r"(SHAPE_CACHE_BYTES), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void shape_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(SH_THREADS, 1)
 k_shape_fwd(int n, HandSrc src, const float* __restrict__ A, const float* __restrict__ W4,
             const float* __restrict__ Sv, const float4* __restrict__ cache, float* __restrict__ verts) {
     extern __shared__ float4 smem4[];
-    float4* sW4 = smem4;
-    float4 (*sA)[48] = reinterpret_cast<float4 (*)[48]>(sW4 + 4 * NV);
-    float (*sBeta)[12] = reinterpret_cast<float (*)[12]>(sA + SH_HPC);
-    __shared__ float4 sT[SH_HPC][NJ];                       // translation columns a_j of this CTA's hands
+    float4* ring = smem4;                                                             // [SHF_STAGES][3 * NV]
+    float4 (*sT)[NJ] = reinterpret_cast<float4 (*)[NJ]>(ring + SHF_STAGES * 3 * NV);  // [SHF_HPC][16] translation columns
+    float (*sBeta)[12] = reinterpret_cast<float (*)[12]>(sT + SHF_HPC);               // [SHF_HPC][12]
+    __shared__ __align__(8) unsigned long long bars[SHF_STAGES];
     const int tid = threadIdx.x;
-    const int h0 = blockIdx.x * SH_HPC, nh = min(SH_HPC, n - h0);
-    stage_hands(n, h0, nh, src, A, W4, sW4, sA, sBeta);
-    __syncthreads();
+    const int h0 = blockIdx.x * SHF_HPC, nh = min(SHF_HPC, n - h0);
+    if (tid == 0) {
+        for (int k = 0; k < SHF_STAGES; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bars[k])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < SHF_STAGES && k < nh; ++k) shape_issue(cache, (size_t)h0 + k, ring + k * 3 * NV, &bars[k]);
+    }
+    // per-hand scalars while the first copies fly
     for (int i = tid; i < nh * NJ; i += SH_THREADS) {
         const int hh = i / NJ, j = i % NJ;
-        sT[hh][j] = make_float4(sA[hh][j * 3].w, sA[hh][j * 3 + 1].w, sA[hh][j * 3 + 2].w, 0.f);
+        const float* a = A + ((size_t)(h0 + hh) * NJ + j) * 12;
+        sT[hh][j] = make_float4(a[3], a[7], a[11], 0.f);
     }
-    __syncthreads();
-    for (int v = tid; v < NV; v += SH_THREADS) {
-        float sv[32];
-        load_shape_row(Sv, v, sv);
-        float4 row[3];
+    for (int i = tid; i < nh * NB; i += SH_THREADS) {
+        const int h = h0 + i / NB, k = i % NB;
+        sBeta[i / NB][k] = src.params[(size_t)(h >> 1) * PD + P_SHAPE + NB * (h & 1) + k];
+    }
+    // this thread's two vertices: weights and shape directions in registers
+    float w[SH_ITEMS_F][NJ], sv[SH_ITEMS_F][32];
+    int vv[SH_ITEMS_F];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) row[r] = cache[((size_t)h0 * 3 + r) * NV + v];
-        for (int hh = 0; hh < nh; ++hh) {
-            const size_t h = h0 + hh;
-            float4 nxt[3];                                   // the next hand's rows fly while this one is computed
-            if (hh + 1 < nh) {
+    for (int sl = 0; sl < SH_ITEMS_F; ++sl) {
+        vv[sl] = min(tid + sl * SH_THREADS, NV - 1);          // out-of-range slots compute a duplicate and do not store
+        load_shape_row(Sv, vv[sl], sv[sl]);
 #pragma unroll
-                for (int r = 0; r < 3; ++r) nxt[r] = cache[((h + 1) * 3 + r) * NV + v];
-            }
-            const float4* b4 = reinterpret_cast<const float4*>(sBeta[hh]);
-            const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2];
-            const float beta[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-            float u[3], t[3] = {0.f, 0.f, 0.f};
+        for (int t = 0; t < 4; ++t) {
+            const float4 q = reinterpret_cast<const float4*>(W4)[t * NV + vv[sl]];
+            w[sl][t * 4] = q.x; w[sl][t * 4 + 1] = q.y; w[sl][t * 4 + 2] = q.z; w[sl][t * 4 + 3] = q.w;
+        }
+    }
+    __syncthreads();                                          // barriers initialised, sT / sBeta written
+    for (int hh = 0; hh < nh; ++hh) {
+        const size_t h = h0 + hh;
+        const int st = hh % SHF_STAGES;
+        shape_wait(&bars[st], (hh / SHF_STAGES) & 1);
+        const float4* rows = ring + st * 3 * NV;
+        const float4* b4 = reinterpret_cast<const float4*>(sBeta[hh]);
+        const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2];
+        const float beta[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+        float t[SH_ITEMS_F][3];
+#pragma unroll
+        for (int sl = 0; sl < SH_ITEMS_F; ++sl) { t[sl][0] = 0.f; t[sl][1] = 0.f; t[sl][2] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float4 a = sT[hh][j];
+#pragma unroll
+            for (int sl = 0; sl < SH_ITEMS_F; ++sl) { t[sl][0] += w[sl][j] * a.x; t[sl][1] += w[sl][j] * a.y; t[sl][2] += w[sl][j] * a.z; }
+        }
+#pragma unroll
+        for (int sl = 0; sl < SH_ITEMS_F; ++sl) {
+            float u[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 float sb = 0.f;
 #pragma unroll
-                for (int k = 0; k < NB; ++k) sb += sv[a * NB + k] * beta[k];
+                for (int k = 0; k < NB; ++k) sb += sv[sl][a * NB + k] * beta[k];
                 u[a] = sb;
             }
+            if (tid + sl * SH_THREADS < NV) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 w4 = sW4[q * NV + v];
-                const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 a = sT[hh][q * 4 + i];
-                    t[0] += wj[i] * a.x; t[1] += wj[i] * a.y; t[2] += wj[i] * a.z;
+                for (int r = 0; r < 3; ++r) {
+                    const float4 row = rows[r * NV + vv[sl]];
+                    verts[(h * NV + vv[sl]) * 3 + r] = (row.w + t[sl][r]) + (row.x * u[0] + row.y * u[1] + row.z * u[2]);
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-                verts[(h * NV + v) * 3 + r] = (row[r].w + t[r]) + (row[r].x * u[0] + row[r].y * u[1] + row[r].z * u[2]);
-            if (hh + 1 < nh) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) row[r] = nxt[r];
-            }
         }
+        __syncthreads();                                      // every thread is done with this stage
+        if (tid == 0 && hh + SHF_STAGES < nh) shape_issue(cache, h + SHF_STAGES, ring + st * 3 * NV, &bars[st]);
     }
 }
 
@@ -992,7 +1047,7 @@ k_shape_bwd_t(int n, const float* __restrict__ W4, const float* __restrict__ gve
 
 // dX: beta entries = sum_v S_v^T T_v^T g_v (what the blend contraction's backward would deliver), the
 // pose-feature entries are written as zero
-__global__ void __launch_bounds__(SH_THREADS, 2)
+__global__ void __launch_bounds__(SH_THREADS, SH_MINB_B)
 k_shape_bwd_b(int n, const float* __restrict__ Sv, const float4* __restrict__ cache, const float* __restrict__ gverts,
               const float* __restrict__ gtips, float* __restrict__ dX) {
     __shared__ float sPart[SH_WARPS][16];
@@ -1050,12 +1105,14 @@ int launch_shape_prep(const ihmr_model* m, int n, HandSrc src, const float* off,
     return IHMR_OK;
 }
 
+constexpr size_t SHAPE_FWD_SMEM = sizeof(float4) * (SHF_STAGES * 3 * NV + SHF_HPC * NJ) + sizeof(float) * SHF_HPC * 12;
+
 int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
     static unsigned long long configured = 0ull;
-    if (int rc = ensure_dynamic_smem(k_shape_fwd, SHAPE_SMEM, configured)) return rc;
-    k_shape_fwd<<<(n + SH_HPC - 1) / SH_HPC, SH_THREADS, SHAPE_SMEM, st>>>(n, src, A, m->W4, m->Sv,
-                                                                           reinterpret_cast<const float4*>(cache), verts);
+    if (int rc = ensure_dynamic_smem(k_shape_fwd, SHAPE_FWD_SMEM, configured)) return rc;
+    k_shape_fwd<<<(n + SHF_HPC - 1) / SHF_HPC, SH_THREADS, SHAPE_FWD_SMEM, st>>>(n, src, A, m->W4, m->Sv,
+                                                                               reinterpret_cast<const float4*>(cache), verts);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
