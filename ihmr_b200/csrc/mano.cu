@@ -955,145 +955,147 @@ __device__ __forceinline__ void warp_reduce_scatter_16(float (&acc)[16], int lan
 }
 
 constexpr int SH_WARPS = SH_THREADS / 32;
-constexpr int SH_ITEMS = 2;          // vertices per thread and hand (tid, tid + 416)
 
-// gradient of one vertex of one hand: g = gverts (+ fingertip part), optionally the cache rows
-struct ShapeItem {
-    float g[3];
-    float4 row[3];
-};
+// Backward of the shape-only path, one kernel: the translation column of dA (sum_v W[v,j] g_v; the rotation
+// block is written as zero, it only feeds the pose gradients a shape-only stage does not use) and the beta
+// entries of dX (sum_v S_v^T T_v^T g_v, what the blend contraction's backward would deliver; the
+// pose-feature entries are written as zero).  Two hands per stage — their caches (2 x 37,344 B) and vertex
+// gradients (18,672 B, 16-byte aligned only for an even hand) arrive by two TMA bulk copies — two stages.
+constexpr int SHB_STAGES = 2;
+constexpr int SHB_HPC = 16;                                                    // hands per CTA (even)
+constexpr uint32_t SHB_G_BYTES = 2 * NV * 3 * sizeof(float);                   // 18,672
+constexpr int SHB_STAGE_F4 = 2 * 3 * NV + (int)(SHB_G_BYTES / 16);             // float4 per stage
+static_assert(SHB_G_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-template <bool ROWS>
-__device__ __forceinline__ void fetch_item(ShapeItem& it, size_t h, int v, const float* __restrict__ gverts,
-                                           const float* __restrict__ gtips, const float4* __restrict__ cache) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) it.g[c] = 0.f;
-    if (v >= NV) return;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) it.g[c] = gverts[(h * NV + v) * 3 + c];
-    if (gtips) {
-        const int tip = (v == 744) ? 0 : (v == 320) ? 1 : (v == 443) ? 2 : (v == 554) ? 3 : (v == 671) ? 4 : -1;
-        if (tip >= 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) it.g[c] += gtips[(h * 5 + tip) * 3 + c];
-        }
-    }
-    if (ROWS) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) it.row[r] = cache[(h * 3 + r) * NV + v];
-    }
+__device__ __forceinline__ void shape_issue_pair(const float4* cache, const float* gverts, size_t h, float4* stage,
+                                                 unsigned long long* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(2 * SHAPE_CACHE_BYTES + SHB_G_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(stage)), "l"(cache + h * 3 * NV), "r"(2 * SHAPE_CACHE_BYTES), "r"(b) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(stage + 2 * 3 * NV)), "l"(gverts + h * NV * 3), "r"(SHB_G_BYTES), "r"(b) : "memory");
 }
 
-// dA: translation column = sum_v W[v,j] g_v; the rotation block is written as zero (it only feeds the pose
-// gradients, which a shape-only stage does not use)
-__global__ void __launch_bounds__(SH_THREADS, 2)
-k_shape_bwd_t(int n, const float* __restrict__ W4, const float* __restrict__ gverts, const float* __restrict__ gtips,
-              float* __restrict__ dA) {
+__global__ void __launch_bounds__(SH_THREADS, 1)
+k_shape_bwd(int n, const float* __restrict__ W4, const float* __restrict__ Sv, const float4* __restrict__ cache,
+            const float* __restrict__ gverts, const float* __restrict__ gtips, float* __restrict__ dA,
+            float* __restrict__ dX) {
     extern __shared__ float4 smem4[];
-    float4* sW4 = smem4;                                                    // [4][778]
-    float* sPart = reinterpret_cast<float*>(sW4 + 4 * NV);                   // [SH_WARPS][48]
+    float4* ring = smem4;                                                          // [SHB_STAGES][SHB_STAGE_F4]
+    float* sPart = reinterpret_cast<float*>(ring + SHB_STAGES * SHB_STAGE_F4);      // [2][SH_WARPS][64]: 48 dta + 16 dbeta
+    float* sTips = sPart + 2 * SH_WARPS * 64;                                       // [SHB_HPC][16]
+    __shared__ __align__(8) unsigned long long bars[SHB_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h0 = blockIdx.x * SH_HPC, nh = min(SH_HPC, n - h0);
-    {
-        const float4* w = reinterpret_cast<const float4*>(W4);
-        for (int i = tid; i < 4 * NV; i += SH_THREADS) sW4[i] = w[i];
+    const int h0 = blockIdx.x * SHB_HPC, nh = min(SHB_HPC, n - h0), npair = nh / 2;
+    if (tid == 0) {
+        for (int k = 0; k < SHB_STAGES; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bars[k])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < SHB_STAGES && k < npair; ++k)
+            shape_issue_pair(cache, gverts, (size_t)h0 + 2 * k, ring + k * SHB_STAGE_F4, &bars[k]);
     }
-    __syncthreads();
-    ShapeItem cur, nxt;
-    fetch_item<false>(cur, h0, tid, gverts, gtips, nullptr);
-    for (int hh = 0; hh < nh; ++hh) {
-        const size_t h = h0 + hh;
-        float acc[48];
+    for (int i = tid; i < nh * 15; i += SH_THREADS) sTips[(i / 15) * 16 + i % 15] = gtips ? gtips[(size_t)h0 * 15 + i] : 0.f;
+    float sv[2][32];
+    int vv[2], tip[2];
 #pragma unroll
-        for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+    for (int sl = 0; sl < 2; ++sl) {
+        const int v = tid + sl * SH_THREADS;
+        vv[sl] = min(v, NV - 1);
+        load_shape_row(Sv, vv[sl], sv[sl]);
+        tip[sl] = (v == 744) ? 0 : (v == 320) ? 1 : (v == 443) ? 2 : (v == 554) ? 3 : (v == 671) ? 4 : -1;
+    }
+    const float4* W44 = reinterpret_cast<const float4*>(W4);
+    __syncthreads();                                            // barriers initialised, tips staged
+    for (int p = 0; p < npair; ++p) {
+        const int st = p % SHB_STAGES;
+        shape_wait(&bars[st], (p / SHB_STAGES) & 1);
+        const float4* stage = ring + st * SHB_STAGE_F4;
+        const float* G = reinterpret_cast<const float*>(stage + 2 * 3 * NV);
 #pragma unroll
-        for (int sl = 0; sl < SH_ITEMS; ++sl) {
-            const int v = tid + sl * SH_THREADS;
-            // next item: the other vertex of this hand, or the first vertex of the next hand
-            if (sl + 1 < SH_ITEMS) fetch_item<false>(nxt, h, v + SH_THREADS, gverts, gtips, nullptr);
-            else if (hh + 1 < nh) fetch_item<false>(nxt, h + 1, tid, gverts, gtips, nullptr);
-            if (v < NV) {
+        for (int hl = 0; hl < 2; ++hl) {
+            const int hh = 2 * p + hl;
+            const float4* rows = stage + hl * 3 * NV;
+            float g[2][3];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const bool ok = tid + sl * SH_THREADS < NV;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[sl][c] = ok ? G[(hl * NV + vv[sl]) * 3 + c] : 0.f;
+                if (tip[sl] >= 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) g[sl][c] += sTips[hh * 16 + tip[sl] * 3 + c];
+                }
+            }
+            // d beta: q = T^T g is the gradient of the shaped (unposed) vertex
+            float accb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) accb[i] = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const float4 r0 = rows[vv[sl]], r1 = rows[NV + vv[sl]], r2 = rows[2 * NV + vv[sl]];
+                const float q[3] = {r0.x * g[sl][0] + r1.x * g[sl][1] + r2.x * g[sl][2],
+                                    r0.y * g[sl][0] + r1.y * g[sl][1] + r2.y * g[sl][2],
+                                    r0.z * g[sl][0] + r1.z * g[sl][1] + r2.z * g[sl][2]};
+#pragma unroll
+                for (int k = 0; k < NB; ++k) accb[k] += sv[sl][k] * q[0] + sv[sl][NB + k] * q[1] + sv[sl][2 * NB + k] * q[2];
+            }
+            warp_reduce_scatter_16(accb, lane);
+            if ((lane & 1) == 0)
+                sPart[(hl * SH_WARPS + warp) * 64 + 48 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = accb[0];
+            // d a_j: sum_v W[v,j] g_v
+            float acc[48];
+#pragma unroll
+            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const float4 w4 = sW4[t * NV + v];
+                    const float4 w4 = W44[t * NV + vv[sl]];
                     const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int r = 0; r < 3; ++r) acc[(t * 4 + i) * 3 + r] += wj[i] * cur.g[r];
+                        for (int r = 0; r < 3; ++r) acc[(t * 4 + i) * 3 + r] += wj[i] * g[sl][r];
                 }
             }
-            cur = nxt;
-        }
-        warp_reduce_scatter_48(acc, lane);
-        if ((lane & 1) == 0) {
-            const int seg = ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + ((lane >> 1) & 1) * 3;
+            warp_reduce_scatter_48(acc, lane);
+            if ((lane & 1) == 0) {
+                const int seg = ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + ((lane >> 1) & 1) * 3;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) sPart[warp * 48 + seg + i] = acc[i];
+                for (int i = 0; i < 3; ++i) sPart[(hl * SH_WARPS + warp) * 64 + seg + i] = acc[i];
+            }
         }
-        __syncthreads();
-        if (tid < 192) {
+        __syncthreads();                                        // partial sums visible, the stage is free
+        if (tid == 0 && p + SHB_STAGES < npair)
+            shape_issue_pair(cache, gverts, (size_t)h0 + 2 * (p + SHB_STAGES), ring + st * SHB_STAGE_F4, &bars[st]);
+        for (int i = tid; i < 2 * (192 + KP); i += SH_THREADS) {
+            const int hl = i / (192 + KP), x = i % (192 + KP);
+            const size_t h = (size_t)h0 + 2 * p + hl;
+            const float* part = sPart + hl * SH_WARPS * 64;
             float sum = 0.f;
-            if ((tid & 3) == 3) {
-                const int e = (tid / 12) * 3 + (tid % 12) / 4;
+            if (x < 192) {
+                if ((x & 3) == 3) {
+                    const int e = (x / 12) * 3 + (x % 12) / 4;
 #pragma unroll
-                for (int w = 0; w < SH_WARPS; ++w) sum += sPart[w * 48 + e];
+                    for (int w = 0; w < SH_WARPS; ++w) sum += part[w * 64 + e];
+                }
+                dA[h * 192 + x] = sum;
+            } else {
+                const int k = x - 192;
+                if (k >= NPF && k < NPF + NB) {
+#pragma unroll
+                    for (int w = 0; w < SH_WARPS; ++w) sum += part[w * 64 + 48 + (k - NPF)];
+                }
+                dX[h * KP + k] = sum;
             }
-            dA[h * 192 + tid] = sum;
         }
-        __syncthreads();
-    }
-}
-
-// dX: beta entries = sum_v S_v^T T_v^T g_v (what the blend contraction's backward would deliver), the
-// pose-feature entries are written as zero
-__global__ void __launch_bounds__(SH_THREADS, SH_MINB_B)
-k_shape_bwd_b(int n, const float* __restrict__ Sv, const float4* __restrict__ cache, const float* __restrict__ gverts,
-              const float* __restrict__ gtips, float* __restrict__ dX) {
-    __shared__ float sPart[SH_WARPS][16];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h0 = blockIdx.x * SH_HPC, nh = min(SH_HPC, n - h0);
-    ShapeItem cur, nxt;
-    fetch_item<true>(cur, h0, tid, gverts, gtips, cache);
-    for (int hh = 0; hh < nh; ++hh) {
-        const size_t h = h0 + hh;
-        float accb[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) accb[i] = 0.f;
-#pragma unroll
-        for (int sl = 0; sl < SH_ITEMS; ++sl) {
-            const int v = tid + sl * SH_THREADS;
-            if (sl + 1 < SH_ITEMS) fetch_item<true>(nxt, h, v + SH_THREADS, gverts, gtips, cache);
-            else if (hh + 1 < nh) fetch_item<true>(nxt, h + 1, tid, gverts, gtips, cache);
-            if (v < NV) {
-                // q = T^T g, the gradient of the shaped (unposed) vertex
-                const float q[3] = {cur.row[0].x * cur.g[0] + cur.row[1].x * cur.g[1] + cur.row[2].x * cur.g[2],
-                                    cur.row[0].y * cur.g[0] + cur.row[1].y * cur.g[1] + cur.row[2].y * cur.g[2],
-                                    cur.row[0].z * cur.g[0] + cur.row[1].z * cur.g[1] + cur.row[2].z * cur.g[2]};
-                float sv[32];
-                load_shape_row(Sv, v, sv);
-#pragma unroll
-                for (int k = 0; k < NB; ++k) accb[k] += sv[k] * q[0] + sv[NB + k] * q[1] + sv[2 * NB + k] * q[2];
-            }
-            cur = nxt;
-        }
-        warp_reduce_scatter_16(accb, lane);
-        if ((lane & 1) == 0) sPart[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = accb[0];
-        __syncthreads();
-        if (tid < KP) {
-            float sum = 0.f;
-            if (tid >= NPF && tid < NPF + NB) {
-#pragma unroll
-                for (int w = 0; w < SH_WARPS; ++w) sum += sPart[w][tid - NPF];
-            }
-            dX[h * KP + tid] = sum;
-        }
-        __syncthreads();
+        __syncthreads();                                        // sPart is rewritten by the next pair
     }
 }
 
 constexpr size_t SHAPE_SMEM = sizeof(float4) * (4 * NV + SH_HPC * 48) + sizeof(float) * SH_HPC * 12;
-constexpr size_t SHAPE_BWD_SMEM = sizeof(float4) * 4 * NV + sizeof(float) * SH_WARPS * 48;
+constexpr size_t SHAPE_BWD_SMEM = sizeof(float4) * SHB_STAGES * SHB_STAGE_F4 + sizeof(float) * (2 * SH_WARPS * 64 + SHB_HPC * 16);
 
 int launch_shape_prep(const ihmr_model* m, int n, HandSrc src, const float* off, const float* A, float* cache, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
@@ -1120,12 +1122,11 @@ int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, co
 int launch_shape_bwd(const ihmr_model* m, int n, const float* cache, const float* gverts, const float* gtips, float* dA,
                      float* dX, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
+    if (n & 1) { set_error("shape_bwd: the hands come in pairs (two per frame)"); return IHMR_E_INVALID; }
     static unsigned long long configured = 0ull;
-    if (int rc = ensure_dynamic_smem(k_shape_bwd_t, SHAPE_BWD_SMEM, configured)) return rc;
-    const int grid = (n + SH_HPC - 1) / SH_HPC;
-    k_shape_bwd_t<<<grid, SH_THREADS, SHAPE_BWD_SMEM, st>>>(n, m->W4, gverts, gtips, dA);
-    IHMR_LAUNCH_OK();
-    k_shape_bwd_b<<<grid, SH_THREADS, 0, st>>>(n, m->Sv, reinterpret_cast<const float4*>(cache), gverts, gtips, dX);
+    if (int rc = ensure_dynamic_smem(k_shape_bwd, SHAPE_BWD_SMEM, configured)) return rc;
+    k_shape_bwd<<<(n + SHB_HPC - 1) / SHB_HPC, SH_THREADS, SHAPE_BWD_SMEM, st>>>(n, m->W4, m->Sv, reinterpret_cast<const float4*>(cache),
+                                                                               gverts, gtips, dA, dX);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
