@@ -15,6 +15,7 @@ Fixtures (float32 .npz, a few hundred KB in total):
                    (4 x 25 = 100 iterations), save_mid_freq=10        -> inputs + 13 result keys
   loop_b2_short.npz  two frames, epoch=3, save_mid_freq=2              -> inputs + results
   loop_collision_short.npz  one near-coincident frame (cfg5 style), epoch=3, save_mid_freq=1
+  loop_mixed6.npz  six frames (three typical, three near-coincident), epoch=8, save_mid_freq=4
   leaves.npz       MANO leaf fwd (8 hands) and SDFLoss fwd/grad (2 frames) from the oracle leaves
 """
 import os
@@ -61,11 +62,19 @@ def run_loop(data, epochs, freq):
     return out
 
 
+def mixed6(layer):
+    a, b = frames(7, 3, "typical", layer), frames(512, 3, "collision", layer)
+    return {k: np.concatenate([a[k], b[k]]) for k in a}
+
+
 def main():
     torch.manual_seed(0)
     S.write_mano_pkls(MODEL_ROOT, seed=0)
     layer = MO.create(os.path.join(MODEL_ROOT, "MANO_RIGHT.pkl"), "mano", use_pca=False, is_rhand=True)
     left = MO.create(os.path.join(MODEL_ROOT, "MANO_LEFT.pkl"), "mano", use_pca=False, is_rhand=False)
+    if "--only-mixed6" in sys.argv:       # added later in the round; the other fixtures are left untouched
+        np.savez_compressed(os.path.join(OUT, "loop_mixed6.npz"), **run_loop(mixed6(layer), 8, 4))
+        return
 
     # leaves
     g = torch.Generator().manual_seed(1)
@@ -96,6 +105,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "loop_collision_short.npz"),
                         **run_loop(frames(0, 1, "collision", layer), 3, 1))
     np.savez_compressed(os.path.join(OUT, "loop_cfg1.npz"), **run_loop(frames(0, 1, "typical", layer), 24, 10))
+    np.savez_compressed(os.path.join(OUT, "loop_mixed6.npz"), **run_loop(mixed6(layer), 8, 4))
 
 
 if __name__ == "__main__":

@@ -186,7 +186,7 @@ def test_value_and_grad_vs_oracle(model_root, oracle_layers, stage_id, mode):
 
 
 # ------------------------------------------------------------------------- whole loop
-@pytest.mark.parametrize("fixture", ["loop_b2_short.npz", "loop_collision_short.npz", "loop_cfg1.npz"])
+@pytest.mark.parametrize("fixture", ["loop_b2_short.npz", "loop_collision_short.npz", "loop_cfg1.npz", "loop_mixed6.npz"])
 def test_full_loop_vs_golden(model_root, fixture):
     """The fixtures were produced by the UNMODIFIED reference host loop + oracle leaves."""
     from ihmr_b200.optimize_model import OptimizeModel
