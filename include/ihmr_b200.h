@@ -142,8 +142,13 @@ typedef struct {
     const float* hand_type_array;   /* (B,2) collision mask: sum > 1.5 */
 } ihmr_targets_t;
 
+/* About 159 KB per frame (10.4 GB at 65536 frames): layer intermediates, vertices and their gradients,
+ * optimiser state, and the per-vertex transform cache of the shape-only stages. */
 size_t ihmr_opt_workspace_bytes(int n_frames);
-/* params (B,122) is read and updated in place; bs_norm is the batch size every batch-mean loss
+/* Stages that update only the global orientations or only the shape coefficients run on specialised
+ * kernels (rigid / affine rewrites of the same layer, equal to rounding); the environment variable
+ * IHMR_B200_GENERIC_STAGES=1 keeps every stage on the generic kernel chain (tests compare the two).
+ * params (B,122) is read and updated in place; bs_norm is the batch size every batch-mean loss
  * divides by (the reference's opt.batchSize), independent of how frames are sharded. */
 int ihmr_opt_stage(const ihmr_model_t* model, int n_frames, int bs_norm, float* params,
                    const ihmr_targets_t* targets, const ihmr_stage_t* stage, int save_mid_freq,
