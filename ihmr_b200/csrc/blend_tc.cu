@@ -224,6 +224,158 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(TMEM_COLS) : "memory");
 }
 
+// ------------------------------------------------------------------ skinning blend on the tensor cores
+// T[v, (h,e)] = sum_j W[v,j] A[h][j][e] is a (778 x 16) . (16 x 12 H) contraction: 7 vertex tiles of 128
+// rows (the constant operand, split hi/lo once per CTA and kept in shared memory for its lifetime) against the
+// joint transforms of 16 hands (N = 192 columns, restaged per group), 2 K-steps x 3 MMAs per tile.  The
+// accumulators of two tiles live in TMEM (2 x 192 of 512 columns) so that the MMAs of tile t+2 overlap the
+// epilogue of tile t+1; the epilogue reads a vertex's twelve T entries per hand with tcgen05.ld, applies them to
+// the posed vertex and writes the skinned vertex.  Persistent CTAs (one per SM) stride over the hand groups.
+constexpr int SKT_THREADS = 512;          // 16 warps: lane quarter = warp % 4, hands 4 * (warp / 4) .. + 3
+constexpr int SKT_HANDS = 16;             // hands per group = MMA N / 12
+constexpr int SKT_N = SKT_HANDS * 12;     // 192
+constexpr int SKT_TILES = (NV + TC_BM - 1) / TC_BM;       // 7
+constexpr uint32_t SKT_SBO = 4 * TC_LBO;  // K = 16: four 16-byte K-columns per 8-row group
+constexpr uint32_t SKT_W_TILE = TC_BM * NJ * 4;           // bytes of one 128 x 16 operand tile (8 KB)
+constexpr uint32_t SKT_B_BYTES = SKT_N * NJ * 4;          // 12 KB
+
+__device__ __forceinline__ uint64_t umma_desc_k16(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((TC_LBO >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((SKT_SBO >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__global__ void __launch_bounds__(SKT_THREADS, 1)
+k_skin_fwd_tc(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
+              const float* __restrict__ W4, float* __restrict__ verts) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* w_hi = smem;                                   // [7][128 x 16]
+    unsigned char* w_lo = w_hi + SKT_TILES * SKT_W_TILE;
+    unsigned char* b_hi = w_lo + SKT_TILES * SKT_W_TILE;          // [192 x 16]
+    unsigned char* b_lo = b_hi + SKT_B_BYTES;
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the constant operand: W4[kc][v] is exactly the 16-byte K-column kc of row v
+    for (int it = tid; it < SKT_TILES * TC_BM * 4; it += SKT_THREADS) {
+        const int kc = it & 3, v = it >> 2, t = v >> 7, r = v & 127;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < NV) w = reinterpret_cast<const float4*>(W4)[kc * NV + v];
+        const uint32_t o = t * SKT_W_TILE + (r >> 3) * SKT_SBO + kc * TC_LBO + (r & 7) * 16;
+        split_store(w, reinterpret_cast<float4*>(w_hi + o), reinterpret_cast<float4*>(w_lo + o));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = umma_idesc(SKT_N);
+    uint32_t phase = 0u;                                      // bit b: parity of the next completion of mbar[b]
+    const int quarter = warp & 3, hsub = warp >> 2;
+
+    auto issue_tile = [&](int t) {                            // one thread: 2 K-steps x 3 MMAs into buffer t & 1
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_d + (uint32_t)((t & 1) * 256);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t koff = ks * 2 * TC_LBO;
+            const uint64_t ah = umma_desc_k16(smem_u32(w_hi) + t * SKT_W_TILE + koff), al = umma_desc_k16(smem_u32(w_lo) + t * SKT_W_TILE + koff);
+            const uint64_t bh = umma_desc_k16(smem_u32(b_hi) + koff), bl = umma_desc_k16(smem_u32(b_lo) + koff);
+            umma_tf32(d, ah, bh, idesc, ks > 0);
+            umma_tf32(d, al, bh, idesc, true);
+            umma_tf32(d, ah, bl, idesc, true);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar[t & 1])) : "memory");
+    };
+
+    const int ngroups = (n + SKT_HANDS - 1) / SKT_HANDS;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int h0 = grp * SKT_HANDS, nh = min(SKT_HANDS, n - h0);
+        // B operand: row (hh, e), K = joint: A[h][j][e] gathered along j
+        for (int it = tid; it < SKT_N * 4; it += SKT_THREADS) {
+            const int kc = it & 3, row = it >> 2, hh = row / 12, e = row - hh * 12;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hh < nh) {
+                const float* a = A + ((size_t)(h0 + hh) * NJ + kc * 4) * 12 + e;
+                v = make_float4(a[0], a[12], a[24], a[36]);
+            }
+            const uint32_t o = (row >> 3) * SKT_SBO + kc * TC_LBO + (row & 7) * 16;
+            split_store(v, reinterpret_cast<float4*>(b_hi + o), reinterpret_cast<float4*>(b_lo + o));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) { issue_tile(0); issue_tile(1); }
+        for (int t = 0; t < SKT_TILES; ++t) {
+            const int buf = t & 1;
+            const int v = t * TC_BM + quarter * 32 + lane;
+            const bool vok = v < NV;
+            // this thread's posed vertices of its four hands: in flight before the accumulator is awaited
+            float vp[4][3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int hh = hsub * 4 + q;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    vp[q][c] = (vok && hh < nh) ? vtemp[v * 3 + c] + off[(size_t)(h0 + hh) * LDN + v * 3 + c] : 0.f;
+            }
+            mbar_wait(smem_u32(&mbar[buf]), (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int hh = hsub * 4 + q;
+                uint32_t r[12];
+                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + hh * 12);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr + 4) : "memory");
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]) : "r"(taddr + 8) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (vok && hh < nh) {
+                    float* o = verts + ((size_t)(h0 + hh) * NV + v) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        o[c] = __uint_as_float(r[c * 4 + 0]) * vp[q][0] + __uint_as_float(r[c * 4 + 1]) * vp[q][1] +
+                               __uint_as_float(r[c * 4 + 2]) * vp[q][2] + __uint_as_float(r[c * 4 + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                  // every warp has drained accumulator buffer `buf`
+            if (tid == 0 && t + 2 < SKT_TILES) issue_tile(t + 2);
+        }
+        // all seven commits were awaited: the B operand may be restaged
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(512) : "memory");
+}
+
+int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st) {
+    if (n <= 0) return IHMR_OK;
+    const size_t smem = 2 * (size_t)SKT_TILES * SKT_W_TILE + 2 * SKT_B_BYTES;
+    static unsigned long long configured = 0ull;
+    if (int rc = ensure_dynamic_smem(k_skin_fwd_tc, smem, configured)) return rc;
+    const int ngroups = (n + SKT_HANDS - 1) / SKT_HANDS;
+    k_skin_fwd_tc<<<min(ngroups, m->num_sms), SKT_THREADS, smem, st>>>(n, off, A, m->vtemp, m->W4, verts);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
+}
+
 template <int BN>
 static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st) {
     const size_t smem = (size_t)(2 * TC_BM + 2 * BN) * TC_BK * 4;

@@ -4,6 +4,8 @@
 //
 // Replaces smplx 0.1.28 MANO.forward -> lbs as called at
 // /root/reference/src/models/optimize_model.py:194-200, and its autograd backward.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace ihmr {
@@ -1193,6 +1195,9 @@ int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const f
 
 int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
+    // the tensor-core version is the product path; IHMR_B200_SKIN_SIMT=1 selects the FP32-pipe kernel it replaced
+    const char* simt = getenv("IHMR_B200_SKIN_SIMT");
+    if (!(simt && simt[0] == '1')) return launch_skin_fwd_tc(m, n, off, A, verts, st);
     k_skin_fwd<<<(n + SK_HPC - 1) / SK_HPC, SK_THREADS, 0, st>>>(n, off, A, m->vtemp, m->Wt, verts);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
