@@ -1206,6 +1206,10 @@ int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
                     const float* gtips, float* gposed, float* dA, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
+    // IHMR_B200_SKIN_BWD_TC=1 selects the tensor-core pair of blend_tc.cu (correct, but measured slower than this
+    // FP32-pipe kernel: 4.9 vs 3.0 ms at 131072 hands)
+    const char* tc = getenv("IHMR_B200_SKIN_BWD_TC");
+    if (tc && tc[0] == '1') return launch_skin_bwd_tc(m, n, off, A, gverts, gtips, gposed, dA, st);
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_skin_bwd, SKIN_BWD_SMEM, configured)) return rc;
     k_skin_bwd<<<(n + SK_HPC - 1) / SK_HPC, SKB_THREADS, SKIN_BWD_SMEM, st>>>(n, off, A, m->vtemp, m->W4,
