@@ -82,6 +82,12 @@ def test_mano_backward_vs_oracle(cuda_layers, oracle64, n):
         assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) <= REL_TOL, name
 
 
+def test_mano_forward_fp32_pipe_variant(cuda_layers, oracle64, monkeypatch):
+    """The FP32-pipe skinning forward that the tcgen05 kernel replaced, kept behind IHMR_B200_SKIN_SIMT=1."""
+    monkeypatch.setenv("IHMR_B200_SKIN_SIMT", "1")
+    test_mano_forward_vs_oracle(cuda_layers, oracle64, 33)
+
+
 def test_mano_backward_tensor_core_variant(cuda_layers, oracle64, monkeypatch):
     """The tcgen05 skinning backward (gposed = T^T g, dA = P^T W) kept behind IHMR_B200_SKIN_BWD_TC=1."""
     monkeypatch.setenv("IHMR_B200_SKIN_BWD_TC", "1")
