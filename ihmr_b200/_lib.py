@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("IHMR_B200_LIB", os.path.join(_HERE, "_lib", "libihmr_
 EXPORTS = (
     "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",
     "ihmr_model_update_shapedirs", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
-    "ihmr_mano_backward", "ihmr_sdf_loss", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
+    "ihmr_mano_backward", "ihmr_sdf_workspace_bytes", "ihmr_sdf_loss", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
     "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics",
 )
 KERNEL_CLASSES = ("pose_prep", "blend_fwd", "skin_fwd", "sdf", "frame_loss", "skin_bwd", "blend_bwd", "pose_bwd", "step")
@@ -81,8 +81,10 @@ def load() -> C.CDLL:
     lib.ihmr_mano_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ihmr_mano_backward.restype = i32
     lib.ihmr_mano_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.ihmr_sdf_workspace_bytes.restype = sz
+    lib.ihmr_sdf_workspace_bytes.argtypes = [i32]
     lib.ihmr_sdf_loss.restype = i32
-    lib.ihmr_sdf_loss.argtypes = [vp, i32, vp, vp, vp, vp, vp, f32, vp]
+    lib.ihmr_sdf_loss.argtypes = [vp, i32, vp, vp, vp, vp, vp, f32, vp, sz, vp]
     lib.ihmr_opt_workspace_bytes.restype = sz
     lib.ihmr_opt_workspace_bytes.argtypes = [i32]
     lib.ihmr_opt_stage.restype = i32
@@ -97,7 +99,7 @@ def load() -> C.CDLL:
     lib.ihmr_eval_metrics.restype = i32
     lib.ihmr_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     lib.ihmr_sdf_stats.restype = i32
-    lib.ihmr_sdf_stats.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.ihmr_sdf_stats.argtypes = [vp, i32, vp, vp, vp, vp, sz, vp]
     lib.ihmr_launch_count.restype = C.c_ulonglong
     lib.ihmr_launch_count.argtypes = []
     lib.ihmr_opt_profile_iteration.restype = i32

@@ -287,22 +287,27 @@ int ihmr_mano_backward(const ihmr_model_t* m, int n, const float* global_orient,
     return launch_pose_bwd(m, n, src, w.dA, grad_joints, w.dX, hg, st);
 }
 
+size_t ihmr_sdf_workspace_bytes(int n_frames) { return n_frames > 0 ? sdf_ws_bytes(n_frames) : 0; }
+
 int ihmr_sdf_loss(const ihmr_model_t* m, int n_frames, const float* hand_verts, float* losses, float* per_vert,
-                  float* origin_scale, float* grad_hand_verts, float robustifier, ihmr_stream_t stream) {
-    IHMR_CHECK_ARG(m && n_frames >= 0 && hand_verts && losses);
+                  float* origin_scale, float* grad_hand_verts, float robustifier, void* workspace,
+                  size_t workspace_bytes, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && n_frames >= 0 && hand_verts && losses && (workspace || n_frames == 0));
+    if (workspace_bytes < ihmr_sdf_workspace_bytes(n_frames)) { set_error("workspace too small: %zu < %zu", workspace_bytes, ihmr_sdf_workspace_bytes(n_frames)); return IHMR_E_WORKSPACE; }
     DeviceGuard guard(m->device);
     SdfArgs a;
     a.verts = hand_verts; a.losses = losses; a.per_vert = per_vert; a.origin = origin_scale;
-    a.gverts = grad_hand_verts; a.robustifier = robustifier;
+    a.gverts = grad_hand_verts; a.robustifier = robustifier; a.ws = workspace;
     return launch_sdf(m, n_frames, a, static_cast<cudaStream_t>(stream));
 }
 
 int ihmr_sdf_stats(const ihmr_model_t* m, int n_frames, const float* hand_verts, float* losses, int* stats,
-                   ihmr_stream_t stream) {
-    IHMR_CHECK_ARG(m && n_frames >= 0 && hand_verts && losses && stats);
+                   void* workspace, size_t workspace_bytes, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && n_frames >= 0 && hand_verts && losses && stats && (workspace || n_frames == 0));
+    if (workspace_bytes < ihmr_sdf_workspace_bytes(n_frames)) { set_error("workspace too small: %zu < %zu", workspace_bytes, ihmr_sdf_workspace_bytes(n_frames)); return IHMR_E_WORKSPACE; }
     DeviceGuard guard(m->device);
     SdfArgs a;
-    a.verts = hand_verts; a.losses = losses; a.stats = stats;
+    a.verts = hand_verts; a.losses = losses; a.stats = stats; a.ws = workspace;
     return launch_sdf(m, n_frames, a, static_cast<cudaStream_t>(stream));
 }
 

@@ -78,7 +78,6 @@ struct SdfArgs {
     const float* joints = nullptr;     // (B,2,16,3) or null
     const float* params = nullptr;     // (B,122) or null
     const float* hand_type = nullptr;  // (B,2) or null: loss/grad masked unless both hands present
-    float* losses = nullptr;           // (B)
     float* per_vert = nullptr;         // (B,1556) or null
     float* origin = nullptr;           // (B,1556) or null
     float* gverts = nullptr;           // (B,2,778,3) or null
@@ -88,7 +87,12 @@ struct SdfArgs {
     int skip_grid_mask = 0;            // bit h: skip the direction whose grid hand is h (its loss part and
                                        // the gradients of the other hand are then NOT produced)
     int* stats = nullptr;              // (B,32) debug counters / phase cycles (zeroed by the caller), tests/tools only
+    void* ws = nullptr;                // sdf_ws_bytes(B) of scratch: frame headers, work list, loss parts, spill area
+    float* losses = nullptr;           // (B) or null: mask * (part_0 + part_1) / 4 (one more tiny launch)
 };
+size_t sdf_ws_bytes(int B);
+// (B,2): the sum of rho over the query vertices of each direction of every frame (written by every launch_sdf)
+const float* sdf_ws_parts(void* ws, int B);
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
 
 // per-frame evaluator metrics (eval.cu): out (B,6)

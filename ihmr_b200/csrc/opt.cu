@@ -19,7 +19,8 @@ struct FrameLossArgs {
     const float* verts;           // (B,2,778,3) same frames
     ihmr_targets_t tg;
     float w2d, w3d, wtrans, wshape, wfinger;
-    const float* col_loss;        // (B) unweighted, masked collision loss from the sdf kernel
+    const float* col_loss;        // (B) unweighted, masked collision loss from the sdf kernels, or
+    const float* col_parts;       // (B,2) its two unmasked direction sums (loss = mask * (p0 + p1) / 4)
     const float* gshift_col;      // (B,3) collision gradient w.r.t. the left-hand shift (scaled) or null
     // outputs
     float* gjoints16;             // (B,2,16,3) or null
@@ -236,7 +237,11 @@ __global__ void __launch_bounds__(FL_THREADS) k_frame_loss(FrameLossArgs a) {
     }
     if (t == 0) {
         const float j2d_b = sum2d / 84.0f * a.w2d, j3d_b = sum3d / 126.0f * a.w3d;
-        const float col = a.col_loss ? a.col_loss[b] : 0.f;
+        float col = a.col_loss ? a.col_loss[b] : 0.f;
+        if (a.col_parts) {
+            const float* ht = a.tg.hand_type_array + (size_t)b * 2;
+            col = ((ht[0] + ht[1] > 1.5f) ? 1.0f : 0.0f) * (a.col_parts[b * 2] + a.col_parts[b * 2 + 1]) * 0.25f;
+        }
         if (a.j2d_batch) a.j2d_batch[b] = j2d_b;
         if (a.j3d_batch) a.j3d_batch[b] = j3d_b;
         if (a.loss_parts) {
@@ -365,6 +370,7 @@ struct OptWs {
     float *col_loss, *gshift, *origin, *best, *j2d_b, *j3d_b, *loss_parts;
     float* shape_cache;       // (N, 778, 3) float4: (T_v | T_v c_v) of the shape-only stages
     int* take;
+    void* sdf_ws;             // scratch of the penetration kernels (sdf_ws_bytes)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -400,6 +406,7 @@ static size_t opt_ws_layout(void* base, int B, OptWs* out) {
     w.loss_parts = (float*)take((size_t)B * 6 * 4);
     w.take = (int*)take((size_t)B * 4);
     w.shape_cache = (float*)take((size_t)n * NV * 12 * 4);
+    w.sdf_ws = take(sdf_ws_bytes(B));
     if (out) *out = w;
     return used;
 }
@@ -511,12 +518,13 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     IHMR_TICK(prof, 3);
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
-    sa.losses = w.col_loss; sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
+    sa.ws = w.sdf_ws; sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
     sa.grad_scale = stg->w_collision / (float)bs_norm;
     sa.skip_grid_mask = plan.sdf_skip_grid;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
     IHMR_TICK(prof, 4);
     la.gshift_col = w.gshift;
+    la.col_loss = nullptr; la.col_parts = sdf_ws_parts(w.sdf_ws, B);
     la.gjoints16 = w.gjoints; la.gtips = w.gtips; la.grad = w.grad;
     la.j2d_batch = w.j2d_b; la.j3d_batch = w.j3d_b;
     k_frame_loss<<<B, FL_THREADS, 0, st>>>(la);
@@ -631,7 +639,7 @@ int opt_final(const ihmr_model* m, int B, const float* params, const ihmr_target
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
     sa.losses = collision_loss ? collision_loss : w.col_loss;
-    sa.origin = collision_origin;
+    sa.origin = collision_origin; sa.ws = w.sdf_ws;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
     ihmr_stage_t dflt{};   // default_loss_weights (optimize_model.py:84-92)
     dflt.w_joints_2d = 10.f; dflt.w_joints_3d = 1000.f; dflt.w_trans = 100.f; dflt.w_shape_reg = 0.1f;

@@ -35,8 +35,9 @@ class _SdfFn(torch.autograd.Function):
         need_grad = hand_verts.requires_grad
         grad = torch.empty_like(hv) if need_grad else None
         rob = float(module.robustifier) if module.robustifier else 0.0
+        ws = torch.empty(max(1, model._lib.ihmr_sdf_workspace_bytes(B)), device=dev, dtype=torch.uint8)
         _lib.check(model._lib.ihmr_sdf_loss(model.handle, B, _ptr(hv), _ptr(losses), _ptr(per_vert), _ptr(origin),
-                                            _ptr(grad), rob, _stream(dev)), "ihmr_sdf_loss")
+                                            _ptr(grad), rob, _ptr(ws), ws.numel(), _stream(dev)), "ihmr_sdf_loss")
         ctx.grad = grad
         ctx.mark_non_differentiable(per_vert, origin)
         return losses, per_vert, origin

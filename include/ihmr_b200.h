@@ -97,17 +97,24 @@ int ihmr_gemm_reference_fp32(int M, int N, int K, const float* A, int lda, const
  * voxel kernel and the grid_sample forward/backward behind it.  hand_verts (n,2,778,3) ->
  * losses (n), per_vert (n,1556) [may be NULL], origin_scale (n,1556) metres, right-hand
  * vertices first [may be NULL], grad_hand_verts (n,2,778,3) = d losses[b] / d hand_verts[b]
- * [may be NULL].  robustifier <= 0 means none (the IHMR-OPT path, loss_utils.py:36). */
+ * [may be NULL].  robustifier <= 0 means none (the IHMR-OPT path, loss_utils.py:36).
+ * workspace: ihmr_sdf_workspace_bytes(n_frames) of device scratch (per-frame headers, the work list of
+ * (frame, direction) items, per-direction loss sums, spill area), 256-byte aligned, not shared by
+ * calls that may run concurrently. */
+size_t ihmr_sdf_workspace_bytes(int n_frames);
 int ihmr_sdf_loss(const ihmr_model_t* model, int n_frames, const float* hand_verts, float* losses,
                   float* per_vert, float* origin_scale, float* grad_hand_verts, float robustifier,
-                  ihmr_stream_t stream);
+                  void* workspace, size_t workspace_bytes, ihmr_stream_t stream);
 
-/* Diagnostic variant for tools/tests: same kernel, additionally fills stats (n,32) int32 (zeroed
- * by the caller): per grid hand h in {0,1}: [2h] voxels evaluated, [2h+1] of them by the far
- * (cluster) search, [4+h] query vertices inside the grid box, [9..18] SM cycles thread 0 spent per kernel phase (bbox,
- * mark, normalise, parity, scan, worklist, candidates+tests, classify+far, sample, outputs). */
+/* Diagnostic variant for tools/tests: same kernels, additionally fills stats (n,32) int32 (zeroed
+ * by the caller): per grid hand h in {0,1}: [2h] voxels evaluated, [2h+1] search rounds, [4+h] query
+ * vertices inside the grid box, [16+h] direction finished by the prep kernel (boxes cannot meet);
+ * [6] (voxel, cluster) pairs, [7] exact candidates, [8] marked voxels, [9] ray items, [10] passes,
+ * [11] / [12] ray items / candidates processed in place because the shared-memory queue was full,
+ * [19..27] SM cycles thread 0 spent per phase (mark, face boxes, parity, scan, worklist,
+ * seeds + candidates, exact tests, finish, sample + outputs). */
 int ihmr_sdf_stats(const ihmr_model_t* model, int n_frames, const float* hand_verts, float* losses,
-                   int32_t* stats, ihmr_stream_t stream);
+                   int32_t* stats, void* workspace, size_t workspace_bytes, ihmr_stream_t stream);
 
 /* ---- fused refinement (a1-a13) --------------------------------------------------------
  * One call per strategy stage replaces the body of OptimizeModel.optimize's stage loop

@@ -16,6 +16,9 @@ Fixtures (float32 .npz, a few hundred KB in total):
   loop_b2_short.npz  two frames, epoch=3, save_mid_freq=2              -> inputs + results
   loop_collision_short.npz  one near-coincident frame (cfg5 style), epoch=3, save_mid_freq=1
   loop_mixed6.npz  six frames (three typical, three near-coincident), epoch=8, save_mid_freq=4
+  loop_long_typical.npz / loop_long_collision.npz  one frame each at the SHIPPED strategy length
+                   (opt_default.py:15,34,53,72: epoch=300 per stage = 1,204 Adam steps,
+                   save_mid_freq=10 = 31 snapshots per stage; bash/optimize.sh:33)   [--only-long]
   leaves.npz       MANO leaf fwd (8 hands) and SDFLoss fwd/grad (2 frames) from the oracle leaves
 """
 import os
@@ -72,6 +75,12 @@ def main():
     S.write_mano_pkls(MODEL_ROOT, seed=0)
     layer = MO.create(os.path.join(MODEL_ROOT, "MANO_RIGHT.pkl"), "mano", use_pca=False, is_rhand=True)
     left = MO.create(os.path.join(MODEL_ROOT, "MANO_LEFT.pkl"), "mano", use_pca=False, is_rhand=False)
+    if "--only-long" in sys.argv:         # round 2: the shipped strategy length (minutes of CPU per frame)
+        which = [a.split("=")[1] for a in sys.argv if a.startswith("--which=")] or ["typical", "collision"]
+        for mode in which:
+            start = 3 if mode == "typical" else 600
+            np.savez_compressed(os.path.join(OUT, f"loop_long_{mode}.npz"), **run_loop(frames(start, 1, mode, layer), 300, 10))
+        return
     if "--only-mixed6" in sys.argv:       # added later in the round; the other fixtures are left untouched
         np.savez_compressed(os.path.join(OUT, "loop_mixed6.npz"), **run_loop(mixed6(layer), 8, 4))
         return
