@@ -87,10 +87,14 @@ struct SdfArgs {
     int skip_grid_mask = 0;            // bit h: skip the direction whose grid hand is h (its loss part and
                                        // the gradients of the other hand are then NOT produced)
     int* stats = nullptr;              // (B,32) debug counters / phase cycles (zeroed by the caller), tests/tools only
+    uint16_t* hints = nullptr;         // (B,2,2048) or null: nearest-face seeds carried from one call to the next on the
+                                       // same frames (zeroed by the caller before the first); they change the work, never
+                                       // the values
     void* ws = nullptr;                // sdf_ws_bytes(B) of scratch: frame headers, work list, loss parts, spill area
     float* losses = nullptr;           // (B) or null: mask * (part_0 + part_1) / 4 (one more tiny launch)
 };
 size_t sdf_ws_bytes(int B);
+size_t sdf_hint_bytes(int B);
 // (B,2): the sum of rho over the query vertices of each direction of every frame (written by every launch_sdf)
 const float* sdf_ws_parts(void* ws, int B);
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);

@@ -371,6 +371,7 @@ struct OptWs {
     float* shape_cache;       // (N, 778, 3) float4: (T_v | T_v c_v) of the shape-only stages
     int* take;
     void* sdf_ws;             // scratch of the penetration kernels (sdf_ws_bytes)
+    uint16_t* sdf_hints;      // nearest-face seeds the penetration kernel carries from one iteration to the next
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -407,6 +408,7 @@ static size_t opt_ws_layout(void* base, int B, OptWs* out) {
     w.take = (int*)take((size_t)B * 4);
     w.shape_cache = (float*)take((size_t)n * NV * 12 * 4);
     w.sdf_ws = take(sdf_ws_bytes(B));
+    w.sdf_hints = (uint16_t*)take(sdf_hint_bytes(B));
     if (out) *out = w;
     return used;
 }
@@ -499,7 +501,7 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
 // value + gradient of one iteration into w.grad (and optionally the six batch losses)
 static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* params, const ihmr_targets_t* tg,
                           const ihmr_stage_t* stg, OptWs& w, FrameLossArgs& la, cudaStream_t st,
-                          IterProf* prof = nullptr, IterPlan plan = IterPlan()) {
+                          IterProf* prof = nullptr, IterPlan plan = IterPlan(), bool carry_hints = false) {
     int rc;
     HandSrc src;
     src.params = params;
@@ -518,7 +520,7 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     IHMR_TICK(prof, 3);
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
-    sa.ws = w.sdf_ws; sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
+    sa.ws = w.sdf_ws; sa.hints = carry_hints ? w.sdf_hints : nullptr; sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
     sa.grad_scale = stg->w_collision / (float)bs_norm;
     sa.skip_grid_mask = plan.sdf_skip_grid;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
@@ -549,6 +551,7 @@ int opt_stage(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr
     opt_ws_layout(ws, B, &w);
     IHMR_CUDA_OK(cudaMemsetAsync(w.m, 0, (size_t)B * PD * 4, st));
     IHMR_CUDA_OK(cudaMemsetAsync(w.v, 0, (size_t)B * PD * 4, st));
+    IHMR_CUDA_OK(cudaMemsetAsync(w.sdf_hints, 0, sdf_hint_bytes(B), st));
     const int nthr = 256, nblk = (int)(((size_t)B * PD + nthr - 1) / nthr);
     int snaps = 0;
     for (int j = 0; j <= stg->epoch; ++j) {
@@ -566,7 +569,7 @@ int opt_stage(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr
             la.origin = w.origin; la.best = w.best; la.take = w.take;
             ++snaps;
         }
-        int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, j == 0, snap));
+        int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, j == 0, snap), true);
         if (rc) return rc;
         StepArgs sa{};
         sa.B = B; sa.mask = stg->update_mask; sa.optimizer = optimizer; sa.lr = stg->lr;
@@ -595,9 +598,10 @@ int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params
     for (auto& e : prof.ev) IHMR_CUDA_OK(cudaEventCreate(&e));
     FrameLossArgs la = base_loss_args(B, bs_norm, params, tg, stg, w);
     // one untimed full iteration fills every cached buffer, then the steady-state iteration is timed
-    int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, true, true));
+    IHMR_CUDA_OK(cudaMemsetAsync(w.sdf_hints, 0, sdf_hint_bytes(B), st));
+    int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, true, true), true);
     if (rc) return rc;
-    rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, &prof, plan_iteration(stg->update_mask, false, false));
+    rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, &prof, plan_iteration(stg->update_mask, false, false), true);
     if (rc) return rc;
     StepArgs sa{};
     sa.B = B; sa.mask = stg->update_mask; sa.optimizer = IHMR_OPT_ADAM; sa.lr = 0.f;   // lr 0: parameters unchanged

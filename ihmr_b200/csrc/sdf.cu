@@ -65,6 +65,7 @@ constexpr int QSEG = Q_CAP / SDF_WARPS;   // candidate queue segment of one warp
 static_assert(PHI_CAP <= 65536 && TV <= 32 && V_CHUNK >= TV, "queue entries pack the voxel index into 16 bits");
 constexpr int SDF_SPILL = NV * 8;   // a direction evaluates at most 8 voxels per query vertex
 constexpr int SDF_MAX_GRID = 160 * 8;
+constexpr int SDF_HINTS = 2048;     // nearest-face hints per (frame, direction): one u16 per voxel of an 8 x 16 x 16 block (wraps)
 constexpr int SDF_HDR = 40;         // floats per frame header (see k_sdf_prep)
 constexpr float Q8_TO_D2 = 1.0f / 16384.0f;         // Q8 units squared -> normalised units squared
 constexpr float Q4D2_TO_D2 = 0.25f * Q8_TO_D2;      // qbox_4d2 units -> normalised units squared
@@ -102,6 +103,7 @@ struct __align__(16) SdfSmem {
     uint16_t coloff[G * G];     // exclusive prefix of popc(work)
     uint32_t worklist[PHI_CAP]; // voxels of the current pass as packed Q8 centres: 8x+4 | (8y+4) << 8 | (8z+4) << 16
     uint32_t best[PHI_CAP];     // bit pattern of the best squared distance (>= 0: orders like uint); then phi
+    uint16_t hintw[PHI_CAP];    // face slot behind best (to rounding): next iteration's seed
     uint32_t queue[Q_CAP];      // (voxel index << 16) | face slot;  parity: (face slot << 10) | column
     uint2 cl_box[NCL];          // union of the cluster's face boxes, same packing as fbox
     uint2 fbox[NCL * 32];       // per face (cluster-table order): box quantised outwards to Q8;
@@ -109,8 +111,7 @@ struct __align__(16) SdfSmem {
     float red[4 * SDF_WARPS];
     int region[4];              // lattice bounds of the marked columns: y min, y max, z min, z max
     int scan_warp[SDF_WARPS];
-    uint32_t qn[2];             // fill of the ray-item queue
-    int qcnt[SDF_WARPS];        // per-warp fill of the candidate queue segments
+    int qcnt[SDF_WARPS];        // fill of each warp's segment of the queue
     int item;
 };
 
@@ -260,9 +261,21 @@ __device__ __forceinline__ float voxel_face_dist2(const SdfSmem& s, const ushort
     return pt_tri_dist2(q, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z);
 }
 
-// one exact (voxel, face) test; the result lowers the voxel's best squared distance
+// one exact (voxel, face) test; the result lowers the voxel's best squared distance.  hintw follows the
+// improvements without an ordering guarantee between concurrent improvers: it is a seed, not a result.
 __device__ __forceinline__ void pair_test(SdfSmem& s, const ushort4* __restrict__ cl_tri, int vi, int slot) {
-    atomicMin(&s.best[vi], __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[vi], slot)));
+    const uint32_t bits = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[vi], slot));
+    if (bits < atomicMin(&s.best[vi], bits)) s.hintw[vi] = (uint16_t)slot;
+}
+
+// packed Q8 voxel centre -> index into the hint table: the low bits of (x, y, z), so that a block of
+// 8 x 16 x 16 neighbouring voxels never collides
+__device__ __forceinline__ int hint_index(uint32_t q8) {
+    return (int)(((q8 >> 3) & 7u) | (((q8 >> 11) & 15u) << 3) | (((q8 >> 19) & 15u) << 7));
+}
+// the remaining bits of (x, y, z): an entry is (tag << 11) | (slot + 1), so a voxel only takes its own hint
+__device__ __forceinline__ uint32_t hint_tag(uint32_t q8) {
+    return ((q8 >> 6) & 3u) | (((q8 >> 15) & 1u) << 2) | (((q8 >> 23) & 1u) << 3);
 }
 
 // lattice indices j with 8j + 4 inside the byte range [lo, hi] (a superset of the lattice points inside the
@@ -422,6 +435,7 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
         const uint32_t code = w.items[s.item];
         const int b = (int)(code >> 1), h = (int)(code & 1u), o = 1 - h;
         const ushort4* cl_tri = h ? cl_l : cl_r;
+        uint16_t* hint = a.hints ? a.hints + ((size_t)b * 2 + h) * SDF_HINTS : nullptr;
         const float* hd = w.hdr + (size_t)b * SDF_HDR;
         float cen[3], tlo[3], thi[3], wlo[3], whi[3];
         const float scale = hd[16 * h + 3];
@@ -437,10 +451,23 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
             if (xform && hand == 1) { out[0] = -out[0] + shx; out[1] += shy; out[2] += shz; }
         };
         long long t_prev = clock64();
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        // every warp fills its own segment of s.queue (no atomics); after a barrier all threads walk the segments
+        auto for_each_queued = [&](auto&& fn) {
+            int pre[SDF_WARPS + 1];
+            pre[0] = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < SDF_WARPS; ++w2) pre[w2 + 1] = pre[w2] + s.qcnt[w2];
+            for (int p2 = tid; p2 < pre[SDF_WARPS]; p2 += SDF_THREADS) {
+                int seg = 0, start = 0;
+#pragma unroll
+                for (int w2 = 1; w2 < SDF_WARPS; ++w2) if (p2 >= pre[w2]) { seg = w2; start = pre[w2]; }
+                fn(s.queue[seg * QSEG + (p2 - start)]);
+            }
+        };
 
         for (int i = tid; i < G * G; i += SDF_THREADS) { s.needed[i] = 0u; s.work[i] = 0u; }
         if (tid < 4) s.region[tid] = (tid & 1) ? -1 : G;
-        if (tid == 0) s.qn[0] = 0u;                    // queue of the parity rasterisation
         __syncthreads();
 
         // ---- query vertices: normalised position, voxel corners, mark
@@ -567,6 +594,8 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                 if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
             };
             const int ry0 = s.region[0], ry1 = s.region[1], rz0 = s.region[2], rz1 = s.region[3];
+            uint32_t* rqueue = s.queue + warp * QSEG;
+            int rq = 0;                                          // fill of this warp's segment (warp-uniform)
             for (int c = warp; c < NCL; c += SDF_WARPS) {
                 {   // clusters that miss the (y,z) region of the marked columns are done
                     const uint2 cb = s.cl_box[c];
@@ -582,21 +611,18 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                 // Most faces cover at most 2 x 2 lattice points: those are handled with the warp converged and
                 // one queue reservation per warp and lattice slot; the lattice box of a larger face is spread
                 // over the lanes of its warp.
-                auto push = [&](bool ok, int face, int col) {          // warp-converged
+                auto push = [&](bool ok, int face, int col) {          // warp-converged; the warp owns its queue segment
                     const uint32_t m = __ballot_sync(0xffffffffu, ok);
                     if (m == 0u) return;
-                    const int leader = __ffs(m) - 1;
-                    uint32_t base = 0u;
-                    if (lane == leader) base = atomicAdd(&s.qn[0], (uint32_t)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
                     if (ok) {
-                        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                        if (pos < Q_CAP) s.queue[pos] = ((uint32_t)face << 10) | (uint32_t)col;
+                        const int pos = rq + __popc(m & lt_mask);
+                        if (pos < QSEG) rqueue[pos] = ((uint32_t)face << 10) | (uint32_t)col;
                         else {
                             ray_item(face, col);
                             if (a.stats) atomicAdd(&a.stats[b * 32 + 11], 1);
                         }
                     }
+                    rq += __popc(m);
                 };
                 const bool cover = (j1 >= j0) && (k1 >= k0);
                 const bool small = cover && (j1 - j0 <= 1) && (k1 - k0 <= 1);
@@ -621,12 +647,10 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                     }
                 }
             }
+            if (lane == 0) s.qcnt[warp] = min(rq, QSEG);
+            if (a.stats && lane == 0) atomicAdd(&a.stats[b * 32 + 9], rq);
             __syncthreads();
-            {
-                const int nq = min((int)s.qn[0], Q_CAP);
-                if (a.stats && tid == 0) atomicAdd(&a.stats[b * 32 + 9], (int)s.qn[0]);
-                for (int p2 = tid; p2 < nq; p2 += SDF_THREADS) ray_item(s.queue[p2] >> 10, s.queue[p2] & 1023u);
-            }
+            for_each_queued([&](uint32_t e) { ray_item((int)(e >> 10), (int)(e & 1023u)); });
             __syncthreads();
             SDF_STAT(3)
             // ---- marked & inside, prefix offsets
@@ -680,11 +704,18 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
             for (int v0 = 0; v0 < nvox; v0 += V_CHUNK) {
                 const int v1 = min(nvox, v0 + V_CHUNK);
                 uint32_t* wqueue = s.queue + warp * QSEG;      // candidates of this warp's voxels: no atomics
-                int wq = 0;                                      // fill (warp-uniform)
+                int wq = 0, ncand = 0;                           // fill (warp-uniform), candidates found
                 for (int t0 = v0 + warp * TV; t0 < v1; t0 += SDF_WARPS * TV) {
                     const int nt = min(TV, v1 - t0);
-                    int myseed = 0;
+                    // seeds carried over from the previous iteration of the refinement loop
+                    int myseed = -1;
+                    if (hint && lane < nt) {
+                        const uint32_t q = s.worklist[t0 + lane], e = hint[hint_index(q)];
+                        if ((e >> 11) == hint_tag(q)) myseed = (int)(e & 2047u) - 1;
+                    }
+                    const uint32_t have = __ballot_sync(0xffffffffu, myseed >= 0);
                     for (int k = 0; k < nt; ++k) {
+                        if ((have >> k) & 1u) continue;
                         const uint32_t q = s.worklist[t0 + k];
                         const uint32_t d0 = qbox_4d2(s.cl_box[lane], q);
                         const uint32_t d1 = (lane + 32 < NCL) ? qbox_4d2(s.cl_box[lane + 32], q) : 0xffffffffu;
@@ -708,7 +739,10 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                         kf = __reduce_min_sync(0xffffffffu, kf);
                         if (lane == k) myseed = (int)(kf & 2047u);
                     }
-                    if (lane < nt) s.best[t0 + lane] = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[t0 + lane], myseed));
+                    if (lane < nt) {
+                        s.best[t0 + lane] = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[t0 + lane], myseed));
+                        s.hintw[t0 + lane] = (uint16_t)myseed;
+                    }
                     __syncwarp();
                     for (int k = 0; k < nt; ++k) {
                         const int v = t0 + k;
@@ -720,42 +754,32 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                         const uint32_t m0 = __ballot_sync(0xffffffffu, qbox_4d2(s.cl_box[lane], q) < thr);
                         const uint32_t m1 = __ballot_sync(0xffffffffu, lane + 32 < NCL && qbox_4d2(s.cl_box[min(lane + 32, NCL - 1)], q) < thr);
                         if (a.stats && lane == 0) atomicAdd(&a.stats[b * 32 + 6], __popc(m0) + __popc(m1));
+                        const uint32_t ventry = ((uint32_t)v << 16) | (uint32_t)lane;
                         auto cluster = [&](int c) {
                             const int slot = c * 32 + lane;
-                            const bool ok = qbox_4d2(s.fbox[slot], q) < thr && slot != seed;
+                            const uint2 fb = s.fbox[slot];
+                            const bool ok = qbox_4d2(fb, q) < thr && slot != seed && fb.x < (1u << 24);      // (not an empty table slot)
                             const uint32_t okm = __ballot_sync(0xffffffffu, ok);
-                            if (ok) {
-                                const int pos = wq + __popc(okm & ((1u << lane) - 1u));
-                                if (pos < QSEG) wqueue[pos] = ((uint32_t)v << 16) | (uint32_t)slot;
-                                else {
-                                    pair_test(s, cl_tri, v, slot);          // segment full: test in place
-                                    if (a.stats) atomicAdd(&a.stats[b * 32 + 12], 1);
-                                }
+                            const int n = __popc(okm);
+                            if (wq + n <= QSEG) {                 // warp-uniform
+                                if (ok) wqueue[wq + __popc(okm & lt_mask)] = ventry + ((uint32_t)c << 5);
+                                wq += n;
+                            } else if (ok) {
+                                pair_test(s, cl_tri, v, slot);          // does not fit the segment: test in place
+                                if (a.stats) atomicAdd(&a.stats[b * 32 + 12], 1);
                             }
-                            wq += __popc(okm);
+                            ncand += n;
                         };
                         for (uint32_t mm = m0; mm; mm &= mm - 1u) cluster(__ffs(mm) - 1);
                         for (uint32_t mm = m1; mm; mm &= mm - 1u) cluster(__ffs(mm) + 31);
                     }
                 }
-                if (lane == 0) s.qcnt[warp] = min(wq, QSEG);
-                if (a.stats && lane == 0) atomicAdd(&a.stats[b * 32 + 7], wq);
+                if (lane == 0) s.qcnt[warp] = wq;
+                if (a.stats && lane == 0) atomicAdd(&a.stats[b * 32 + 7], ncand);
                 __syncthreads();
                 SDF_STAT(6)
                 if (a.stats && tid == 0) atomicAdd(&a.stats[b * 32 + 2 * h + 1], 1);
-                {
-                    int pre[SDF_WARPS + 1];
-                    pre[0] = 0;
-#pragma unroll
-                    for (int w2 = 0; w2 < SDF_WARPS; ++w2) pre[w2 + 1] = pre[w2] + s.qcnt[w2];
-                    for (int p2 = tid; p2 < pre[SDF_WARPS]; p2 += SDF_THREADS) {
-                        int seg = 0, start = 0;
-#pragma unroll
-                        for (int w2 = 1; w2 < SDF_WARPS; ++w2) if (p2 >= pre[w2]) { seg = w2; start = pre[w2]; }
-                        const uint32_t e = s.queue[seg * QSEG + (p2 - start)];
-                        pair_test(s, cl_tri, e >> 16, e & 0xffffu);
-                    }
-                }
+                for_each_queued([&](uint32_t e) { pair_test(s, cl_tri, (int)(e >> 16), (int)(e & 0xffffu)); });
                 __syncthreads();
                 SDF_STAT(7)
             }
@@ -764,6 +788,7 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                 const float d = sqrtf(__uint_as_float(s.best[i]));
                 s.best[i] = __float_as_uint(d);
                 if (multi) spill[pass0 + i] = d;
+                if (hint) hint[hint_index(s.worklist[i])] = (uint16_t)((hint_tag(s.worklist[i]) << 11) | (uint32_t)(s.hintw[i] + 1));
             }
             __syncthreads();
             SDF_STAT(8)
@@ -771,38 +796,52 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
 
         // ---- trilinear sample + gradient (grid_sampler_3d fwd/bwd, align_corners=False, zeros) and the
         //      per-vertex outputs of the query hand o
+        const size_t ov0 = (size_t)b * (2 * NV) + o * NV;
+        const bool want_shift = a.gshift && o == 1;
+        if (total == 0) {          // no voxel of the grid hand is both touched and inside: exact zeros
+            const float rho0 = 0.f;                     // rho(0) = 0 with and without the robustifier
+            for (int v = tid; v < NV; v += SDF_THREADS) {
+                if (a.per_vert) a.per_vert[ov0 + v] = rho0;
+                if (a.origin) a.origin[ov0 + v] = 0.f;
+            }
+            if (a.gverts) { float* gp = a.gverts + ov0 * 3; for (int i = tid; i < NV * 3; i += SDF_THREADS) gp[i] = 0.f; }
+            if (tid == 0) w.parts[b * 2 + h] = 0.f;
+            if (want_shift && tid < 3) a.gshift[(size_t)b * 3 + tid] = 0.f;
+            SDF_STAT(9)
+            continue;
+        }
+        // d psi / d vertex = (G/2) * d psi / d(ix) / scale ; loss = sum(rho) / 4
+        const float kbase = mask * a.grad_scale * 0.25f * (0.5f * G) / scale;
         float sums[4] = {0.f, 0.f, 0.f, 0.f};      // sum of rho, gradient sum xyz
 #pragma unroll
         for (int sl = 0; sl < SDF_SLOTS; ++sl) {
             const int v = tid + sl * SDF_THREADS;
             if (v >= NV) continue;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (total > 0) {
-                float fr[3], pv[3];
-                int i0[3];
-                load_vert(o, v, pv);
-                if (locate(pv, fr, i0)) {
-                    const float tx = fr[0], ty = fr[1], tz = fr[2];
+            float fr[3], pv[3];
+            int i0[3];
+            load_vert(o, v, pv);
+            if (locate(pv, fr, i0)) {
+                const float tx = fr[0], ty = fr[1], tz = fr[2];
 #pragma unroll
-                    for (int dz = 0; dz < 2; ++dz)
+                for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
-                        for (int dy = 0; dy < 2; ++dy)
+                    for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                            for (int dx = 0; dx < 2; ++dx) {
-                                const int xc = i0[0] + dx, yc = i0[1] + dy, zc = i0[2] + dz;
-                                if (xc < 0 || xc >= G || yc < 0 || yc >= G || zc < 0 || zc >= G) continue;
-                                const int c = zc * G + yc;
-                                const uint32_t wk = s.work[c];
-                                if (!((wk >> xc) & 1u)) continue;
-                                const int idx = s.coloff[c] + __popc(wk & ((1u << xc) - 1u));
-                                const float val = multi ? spill[idx] : __uint_as_float(s.best[idx]);
-                                const float wx = dx ? tx : 1.0f - tx, wy = dy ? ty : 1.0f - ty, wz = dz ? tz : 1.0f - tz;
-                                acc[0] += val * wx * wy * wz;
-                                acc[1] += (dx ? val : -val) * wy * wz;
-                                acc[2] += (dy ? val : -val) * wx * wz;
-                                acc[3] += (dz ? val : -val) * wx * wy;
-                            }
-                }
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int xc = i0[0] + dx, yc = i0[1] + dy, zc = i0[2] + dz;
+                            if (xc < 0 || xc >= G || yc < 0 || yc >= G || zc < 0 || zc >= G) continue;
+                            const int c = zc * G + yc;
+                            const uint32_t wk = s.work[c];
+                            if (!((wk >> xc) & 1u)) continue;
+                            const int idx = s.coloff[c] + __popc(wk & ((1u << xc) - 1u));
+                            const float val = multi ? spill[idx] : __uint_as_float(s.best[idx]);
+                            const float wx = dx ? tx : 1.0f - tx, wy = dy ? ty : 1.0f - ty, wz = dz ? tz : 1.0f - tz;
+                            acc[0] += val * wx * wy * wz;
+                            acc[1] += (dx ? val : -val) * wy * wz;
+                            acc[2] += (dy ? val : -val) * wx * wz;
+                            acc[3] += (dz ? val : -val) * wx * wy;
+                        }
             }
             const float psi = acc[0];
             float rho = psi, drho = 1.0f;
@@ -812,22 +851,19 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                 drho = 2.0f * t / a.robustifier / ((frac + 1.0f) * (frac + 1.0f));
             }
             sums[0] += rho;
-            const size_t ov = (size_t)b * (2 * NV) + o * NV + v;
-            if (a.per_vert) a.per_vert[ov] = rho;
-            if (a.origin) a.origin[ov] = psi * scale;
+            if (a.per_vert) a.per_vert[ov0 + v] = rho;
+            if (a.origin) a.origin[ov0 + v] = psi * scale;
             if (a.gverts || a.gshift) {
-                // d psi / d vertex = (G/2) * d psi / d(ix) / scale ; loss = sum(rho) / 4
-                const float kk = mask * a.grad_scale * 0.25f * drho * (0.5f * G) / scale;
+                const float kk = kbase * drho;
                 float g[3] = {kk * acc[1], kk * acc[2], kk * acc[3]};
                 sums[1] += g[0]; sums[2] += g[1]; sums[3] += g[2];
                 if (a.gverts) {
                     if (xform && o == 1) g[0] = -g[0];
-                    float* gp = a.gverts + ov * 3;
+                    float* gp = a.gverts + (ov0 + v) * 3;
                     gp[0] = g[0]; gp[1] = g[1]; gp[2] = g[2];
                 }
             }
         }
-        const bool want_shift = a.gshift && o == 1;
         block_sum4(sums, want_shift ? 4 : 1, s.red);
         if (tid == 0) w.parts[b * 2 + h] = sums[0];
         if (want_shift && tid >= 1 && tid < 4) a.gshift[(size_t)b * 3 + (tid - 1)] = sums[tid];
@@ -861,6 +897,8 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     }
     return IHMR_OK;
 }
+
+size_t sdf_hint_bytes(int B) { return (size_t)B * 2 * SDF_HINTS * sizeof(uint16_t); }
 
 const float* sdf_ws_parts(void* ws, int B) { return sdf_ws_carve(ws, B).parts; }
 
