@@ -15,13 +15,14 @@ EXPORTS = (
     "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",
     "ihmr_model_update_shapedirs", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
     "ihmr_mano_backward", "ihmr_sdf_workspace_bytes", "ihmr_sdf_loss", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
-    "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics",
+    "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics", "ihmr_measure_fp32_peak", "ihmr_select_snapshots",
 )
 KERNEL_CLASSES = ("pose_prep", "blend_fwd", "skin_fwd", "sdf", "frame_loss", "skin_bwd", "blend_bwd", "pose_bwd", "step")
 
 P_CAM, P_TRANS, P_R_ORIENT, P_R_POSE, P_L_ORIENT, P_L_POSE, P_R_SHAPE, P_L_SHAPE = (1, 2, 4, 8, 16, 32, 64, 128)
 LOSS_IDS = {"joints_3d_loss_p": 0, "collision_loss": 1, "joints_2d_loss_p": 2}
 OPTIMIZERS = {"adam": 0, "sgd": 1}
+STAGE_GENERIC_KERNELS = 1
 PARAM_MASKS = {
     "pred_cam_params": P_CAM, "pred_hand_trans": P_TRANS, "pred_right_orient": P_R_ORIENT,
     "pred_right_pose_params": P_R_POSE, "pred_left_orient": P_L_ORIENT,
@@ -36,7 +37,7 @@ class Stage(C.Structure):
         ("w_joints_2d", C.c_float), ("w_joints_3d", C.c_float), ("w_trans", C.c_float),
         ("w_shape_reg", C.c_float), ("w_collision", C.c_float), ("w_finger_reg", C.c_float),
         ("n_filters", C.c_int32), ("filter_loss", C.c_int32 * 4), ("filter_percent", C.c_float * 4),
-        ("select_loss", C.c_int32),
+        ("select_loss", C.c_int32), ("flags", C.c_uint32),
     ]
 
 
@@ -98,6 +99,10 @@ def load() -> C.CDLL:
         fn.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
     lib.ihmr_eval_metrics.restype = i32
     lib.ihmr_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp]
+    lib.ihmr_select_snapshots.restype = i32
+    lib.ihmr_select_snapshots.argtypes = [i32, i32, vp, C.POINTER(Stage), vp, vp]
+    lib.ihmr_measure_fp32_peak.restype = i32
+    lib.ihmr_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_float), vp, vp]
     lib.ihmr_sdf_stats.restype = i32
     lib.ihmr_sdf_stats.argtypes = [vp, i32, vp, vp, vp, vp, sz, vp]
     lib.ihmr_launch_count.restype = C.c_ulonglong
@@ -142,4 +147,5 @@ def make_stage(stage: dict) -> Stage:
     if stage["select_loss"] not in LOSS_IDS:
         raise IhmrError(f"criterion {stage['select_loss']!r} is not usable for selection")
     s.select_loss = LOSS_IDS[stage["select_loss"]]
+    s.flags = STAGE_GENERIC_KERNELS if stage.get("generic_kernels") else 0
     return s

@@ -19,6 +19,13 @@ LIB_PATH = os.path.join(OUT_DIR, "libihmr_b200.so")
 SOURCES = ["abi.cu", "mano.cu", "sdf.cu", "opt.cu", "blend_tc.cu", "eval.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "ihmr_b200.h")]
 
+# Extra libraries for the tests: name -> (path, source recompiled with extra flags).  `smallcaps` shrinks the shared-memory
+# capacities of the penetration kernel so that ordinary frames take every multi-pass / overflow branch.
+VARIANTS = {
+    "smallcaps": (os.path.join(OUT_DIR, "libihmr_b200_smallcaps.so"), "sdf.cu",
+                  ["-DSDF_PHI_CAP=64", "-DSDF_Q_CAP=128", "-DSDF_V_CHUNK=16"]),
+}
+
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
@@ -41,11 +48,22 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+def _build_variants(nvcc, ccbin, objs, verbose):
+    for name, (path, src, flags) in VARIANTS.items():
+        obj = os.path.join(OUT_DIR, f"{name}_{src.replace('.cu', '.o')}")
+        cmd = [nvcc, *ccbin, *NVCC_FLAGS, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        others = [o for o in objs if os.path.basename(o) != src.replace(".cu", ".o")]
+        subprocess.check_call([nvcc, *ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", obj, *others, "-o", path])
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     stamp_file = os.path.join(OUT_DIR, "stamp.txt")
     stamp = _stamp()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_file):
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp_file) and all(os.path.exists(v[0]) for v in VARIANTS.values()):
         if open(stamp_file).read().strip() == stamp:
             return LIB_PATH
     nvcc = _nvcc()
@@ -70,6 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     link = [nvcc, *ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB_PATH]
     subprocess.check_call(link)
+    _build_variants(nvcc, ccbin, objs, verbose)
     with open(stamp_file, "w") as fh:
         fh.write(stamp)
     return LIB_PATH

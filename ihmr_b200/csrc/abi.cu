@@ -32,6 +32,7 @@ int opt_final(const ihmr_model* m, int B, const float* params, const ihmr_target
               float* j3d_loss_p, void* ws, cudaStream_t st);
 int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr_targets_t* tg,
                           const ihmr_stage_t* stg, float* ms, void* ws, cudaStream_t st);
+int select_snapshots(int S, int B, const float* crit, const ihmr_stage_t* stg, int* index, cudaStream_t st);
 
 template <typename T>
 static int upload(T** dst, const std::vector<T>& host) {
@@ -317,6 +318,12 @@ int ihmr_eval_metrics(int n_frames, const float* pred_joints_3d, const float* gt
     return launch_eval_metrics(n_frames, pred_joints_3d, gt_joints_3d, collision_origin_scale, scale, out, static_cast<cudaStream_t>(stream));
 }
 
+int ihmr_measure_fp32_peak(const ihmr_model_t* m, float* tflops, void* scratch, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && tflops && scratch);
+    DeviceGuard guard(m->device);
+    return measure_fp32_peak(m->num_sms, tflops, static_cast<float*>(scratch), static_cast<cudaStream_t>(stream));
+}
+
 size_t ihmr_opt_workspace_bytes(int n_frames) { return n_frames > 0 ? opt_ws_bytes(n_frames) : 0; }
 
 static int check_targets(const ihmr_targets_t* t) {
@@ -365,6 +372,15 @@ int ihmr_opt_value_and_grad(const ihmr_model_t* m, int B, int bs_norm, const flo
     if (workspace_bytes < opt_ws_bytes(B)) { set_error("workspace too small: %zu < %zu", workspace_bytes, opt_ws_bytes(B)); return IHMR_E_WORKSPACE; }
     DeviceGuard guard(m->device);
     return opt_value_and_grad(m, B, bs_norm, params, targets, stage, losses6, grad, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_select_snapshots(int n_snapshots, int n_frames, const float* criteria, const ihmr_stage_t* stage, int32_t* index,
+                          ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(n_snapshots > 0 && n_frames >= 0 && criteria && index);
+    int rc;
+    if ((rc = check_stage(stage))) return rc;
+    if (n_frames == 0) return IHMR_OK;
+    return select_snapshots(n_snapshots, n_frames, criteria, stage, index, static_cast<cudaStream_t>(stream));
 }
 
 int ihmr_opt_profile_iteration(const ihmr_model_t* m, int B, int bs_norm, float* params,

@@ -397,184 +397,6 @@ int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float
     return IHMR_OK;
 }
 
-// ------------------------------------------------------------------ skinning backward on the tensor cores
-// Two contractions.  (1) k_skin_fwd_tc<1>: gposed = T_v^T g_v with T from the same W . A^T tiles as the forward.
-// (2) k_skin_bwd_da: dA[h][j][e] = sum_v W[v,j] g_v[r] [v_posed,1][c]  (e = 4 r + c) as
-//     D[(h,e), j] = sum_v P^T[(h,e), v] . W[v, j]:  M = 10 hands x 12 = 120 rows (padded to 128), N = 16 joints,
-//     K = vertices in chunks of 32.  W^T is the constant K-major operand (16 x 800, split hi/lo once per CTA);
-//     the products P are made by the warps (warp = hand, lane = vertex of the chunk), split and stored
-//     transposed into a double-buffered operand whose K-columns are 144 bytes apart so that the 32 lanes of a
-//     warp hit 32 different banks; one accumulator of 16 TMEM columns collects all 25 chunks.
-constexpr int SBD_HANDS = 10;
-constexpr int SBD_THREADS = SBD_HANDS * 32;
-constexpr int SBD_CHUNKS = (NV + 31) / 32;                 // 25
-constexpr uint32_t SBD_A_LBO = 144, SBD_A_SBO = 8 * 144;   // skewed K-columns (conflict-free transposed stores)
-constexpr uint32_t SBD_A_BYTES = 16 * SBD_A_SBO;           // one 128 x 32 operand buffer (hi or lo)
-constexpr uint32_t SBD_B_LBO = 128, SBD_B_SBO = SBD_CHUNKS * 8 * 128;   // 16 x 800: 200 K-columns per 8-row group
-constexpr uint32_t SBD_B_BYTES = 2 * SBD_B_SBO;
-
-__device__ __forceinline__ uint64_t umma_desc_any(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-    d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
-__global__ void __launch_bounds__(SBD_THREADS, 1)
-k_skin_bwd_da(int n, const float* __restrict__ off, const float* __restrict__ vtemp, const float* __restrict__ Wt,
-              const float* __restrict__ gverts, const float* __restrict__ gtips, float* __restrict__ gposed,
-              float* __restrict__ dA) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* b_hi = smem;                                   // W^T, [2][200][8][16 B]
-    unsigned char* b_lo = b_hi + SBD_B_BYTES;
-    unsigned char* a_hi = b_lo + SBD_B_BYTES;                     // [2 buffers][128 x 32]
-    unsigned char* a_lo = a_hi + 2 * SBD_A_BYTES;
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "n"(32) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[1])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // constant operand: element (joint j, vertex v) of W^T, vertices >= 778 are zero
-    for (int it = tid; it < NJ * SBD_CHUNKS * 8; it += SBD_THREADS) {
-        const int j = it / (SBD_CHUNKS * 8), kc = it - j * (SBD_CHUNKS * 8);
-        float4 w;
-        w.x = (kc * 4 + 0 < NV) ? Wt[j * NV + kc * 4 + 0] : 0.f;
-        w.y = (kc * 4 + 1 < NV) ? Wt[j * NV + kc * 4 + 1] : 0.f;
-        w.z = (kc * 4 + 2 < NV) ? Wt[j * NV + kc * 4 + 2] : 0.f;
-        w.w = (kc * 4 + 3 < NV) ? Wt[j * NV + kc * 4 + 3] : 0.f;
-        const uint32_t o = (j >> 3) * SBD_B_SBO + kc * SBD_B_LBO + (j & 7) * 16;
-        split_store(w, reinterpret_cast<float4*>(b_hi + o), reinterpret_cast<float4*>(b_lo + o));
-    }
-    // the padding rows 120..127 of both operand buffers stay zero for the lifetime of the CTA
-    for (int it = tid; it < 4 * (int)SBD_A_BYTES / 4; it += SBD_THREADS) reinterpret_cast<float*>(a_hi)[it] = 0.f;
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_slot;
-    const uint32_t idesc = umma_idesc(NJ);
-    uint32_t phase = 0u;
-
-    const int ngroups = (n + SBD_HANDS - 1) / SBD_HANDS;
-    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const int h0 = grp * SBD_HANDS, nh = min(SBD_HANDS, n - h0);
-        const int hh = warp;                                   // this warp's hand
-        const bool hok = hh < nh;
-        const size_t h = (size_t)h0 + hh;
-        if (hok && lane < LDN - NC) gposed[h * LDN + NC + lane] = 0.f;       // pad columns read by the blend contraction
-        auto fetch = [&](int k, float (&g)[3], float (&pp)[3]) {
-            const int v = k * 32 + lane;
-            const bool ok = hok && v < NV && k < SBD_CHUNKS;
-            const int tip = (v == 744) ? 0 : (v == 320) ? 1 : (v == 443) ? 2 : (v == 554) ? 3 : (v == 671) ? 4 : -1;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                g[c] = (ok && gverts) ? gverts[(h * NV + v) * 3 + c] : 0.f;
-                if (ok && tip >= 0 && gtips) g[c] += gtips[(h * 5 + tip) * 3 + c];
-                pp[c] = ok ? vtemp[v * 3 + c] + off[h * LDN + v * 3 + c] : 0.f;
-            }
-        };
-        float g[3], pp[3], gn[3], ppn[3];
-        fetch(0, g, pp);
-        for (int k = 0; k < SBD_CHUNKS; ++k) {
-            const int b = k & 1;
-            fetch(k + 1, gn, ppn);                             // next chunk's loads fly during this one
-            if (k >= 2) {                                      // the MMAs of chunk k-2 have released buffer b
-                mbar_wait(smem_u32(&mbar[b]), (phase >> b) & 1u);
-                phase ^= 1u << b;
-            }
-            unsigned char* ah = a_hi + b * SBD_A_BYTES;
-            unsigned char* al = a_lo + b * SBD_A_BYTES;
-            const bool live = hok && (k * 32 + lane) < NV;
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int row = hh * 12 + r * 4 + c;
-                    const float x = live ? g[r] * (c < 3 ? pp[c] : 1.0f) : 0.f;
-                    const float xh = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-                    const uint32_t o = (row >> 3) * SBD_A_SBO + (lane >> 2) * SBD_A_LBO + (row & 7) * 16 + (lane & 3) * 4;
-                    *reinterpret_cast<float*>(ah + o) = xh;
-                    *reinterpret_cast<float*>(al + o) = x - xh;
-                }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t dah = umma_desc_any(smem_u32(ah) + ks * 2 * SBD_A_LBO, SBD_A_LBO, SBD_A_SBO);
-                    const uint64_t dal = umma_desc_any(smem_u32(al) + ks * 2 * SBD_A_LBO, SBD_A_LBO, SBD_A_SBO);
-                    const uint32_t bo = (uint32_t)(k * 8 + ks * 2) * SBD_B_LBO;
-                    const uint64_t dbh = umma_desc_any(smem_u32(b_hi) + bo, SBD_B_LBO, SBD_B_SBO);
-                    const uint64_t dbl = umma_desc_any(smem_u32(b_lo) + bo, SBD_B_LBO, SBD_B_SBO);
-                    umma_tf32(tmem_d, dah, dbh, idesc, k > 0 || ks > 0);
-                    umma_tf32(tmem_d, dal, dbh, idesc, true);
-                    umma_tf32(tmem_d, dah, dbl, idesc, true);
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar[b])) : "memory");
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { g[c] = gn[c]; pp[c] = ppn[c]; }
-        }
-        // the last two commits (chunks 23 and 24) cover every MMA of the group
-        mbar_wait(smem_u32(&mbar[1]), (phase >> 1) & 1u); phase ^= 2u;
-        mbar_wait(smem_u32(&mbar[0]), phase & 1u); phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (warp < 4) {
-            const int row = warp * 32 + lane, rh = row / 12, e = row - rh * 12;
-            uint32_t v[16];
-            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (rh < nh) {
-                float* o = dA + ((size_t)h0 + rh) * 192 + e;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) o[j * 12] = __uint_as_float(v[j]);
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                       // accumulator drained before the next group overwrites it
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(32) : "memory");
-}
-
-int launch_skin_bwd_tc(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
-                       const float* gtips, float* gposed, float* dA, cudaStream_t st) {
-    if (n <= 0) return IHMR_OK;
-    {
-        const size_t smem = 2 * (size_t)SKT_TILES * SKT_W_TILE + 2 * SKT_B_BYTES;
-        static unsigned long long configured = 0ull;
-        if (int rc = ensure_dynamic_smem(k_skin_fwd_tc<1>, smem, configured)) return rc;
-        const int ngroups = (n + SKT_HANDS - 1) / SKT_HANDS;
-        k_skin_fwd_tc<1><<<min(ngroups, m->num_sms), SKT_THREADS, smem, st>>>(n, gverts, A, gtips, m->W4, gposed);
-        IHMR_LAUNCH_OK();
-    }
-    const size_t smem = 2 * (size_t)SBD_B_BYTES + 4 * (size_t)SBD_A_BYTES;
-    static unsigned long long configured = 0ull;
-    if (int rc = ensure_dynamic_smem(k_skin_bwd_da, smem, configured)) return rc;
-    const int ngroups = (n + SBD_HANDS - 1) / SBD_HANDS;
-    k_skin_bwd_da<<<min(ngroups, m->num_sms), SBD_THREADS, smem, st>>>(n, off, m->vtemp, m->Wt, gverts, gtips, gposed, dA);
-    IHMR_LAUNCH_OK();
-    return IHMR_OK;
-}
-
 template <int BN>
 static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st) {
     const size_t smem = (size_t)(2 * TC_BM + 2 * BN) * TC_BK * 4;

@@ -105,4 +105,48 @@ int launch_eval_metrics(int B, const float* pred, const float* gt, const float* 
     return IHMR_OK;
 }
 
+// ---- FP32 FMA peak: 8 independent chains per thread, nothing but FFMA in the loop (measurement aid)
+__global__ void __launch_bounds__(256) k_ffma_peak(int iters, float* out) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], m, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456f) out[0] = s;       // keeps the chains alive
+}
+
+int measure_fp32_peak(int num_sms, float* tflops, float* scratch, cudaStream_t st) {
+    const int iters = 4096, blocks = num_sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    IHMR_CUDA_OK(cudaEventCreate(&e0));
+    IHMR_CUDA_OK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, st);
+        k_ffma_peak<<<blocks, threads, 0, st>>>(iters, scratch);
+        cudaEventRecord(e1, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            set_error("fp32 peak measurement failed: %s", cudaGetErrorString(e));
+            return IHMR_E_CUDA;
+        }
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    count_launch();
+    *tflops = 2.0f * 8 * 16 * (float)iters * blocks * threads / (best * 1e-3f) / 1e12f;
+    return IHMR_OK;
+}
+
 }  // namespace ihmr

@@ -56,9 +56,6 @@ int launch_shape_bwd(const ihmr_model* m, int n, const float* cache, const float
                      float* dX, cudaStream_t st);
 // skinning forward with the blend T = W . A^T on tcgen05 (blend_tc.cu)
 int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st);
-// skinning backward on tcgen05: gposed = T^T g and dA = P^T W (blend_tc.cu)
-int launch_skin_bwd_tc(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
-                       const float* gtips, float* gposed, float* dA, cudaStream_t st);
 // C[M,Nc] = A[M,K] . B[Nc,K]^T on tcgen05 with 3xTF32 splitting (blend_tc.cu)
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                        cudaStream_t st);
@@ -102,5 +99,8 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
 // per-frame evaluator metrics (eval.cu): out (B,6)
 int launch_eval_metrics(int B, const float* pred, const float* gt, const float* origin, const float* scale, float* out,
                         cudaStream_t st);
+
+// FP32 FMA throughput of the device in TFLOP/s (synchronises the stream; scratch: >= 4 bytes of device memory)
+int measure_fp32_peak(int num_sms, float* tflops, float* scratch, cudaStream_t st);
 
 }  // namespace ihmr

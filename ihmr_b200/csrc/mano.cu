@@ -4,7 +4,6 @@
 //
 // Replaces smplx 0.1.28 MANO.forward -> lbs as called at
 // /root/reference/src/models/optimize_model.py:194-200, and its autograd backward.
-#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -395,63 +394,7 @@ k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda, const float* 
 }
 
 // -------------------------------------------------------------------------------- skinning
-constexpr int SK_THREADS = 416;   // 13 warps x 2 vertex slots = 832 >= 778
-constexpr int SK_SLOTS = 2;
 constexpr int SK_HPC = 8;         // hands per CTA
-
-__global__ void __launch_bounds__(SK_THREADS, 2)
-k_skin_fwd(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
-           const float* __restrict__ Wt, float* __restrict__ verts) {
-    __shared__ float4 sA[SK_HPC][48];
-    const int tid = threadIdx.x;
-    const int h0 = blockIdx.x * SK_HPC;
-    const int nh = min(SK_HPC, n - h0);
-    float w[SK_SLOTS][NJ], vt[SK_SLOTS][3];
-    int v[SK_SLOTS];
-#pragma unroll
-    for (int s = 0; s < SK_SLOTS; ++s) {
-        v[s] = tid + s * SK_THREADS;
-        const bool ok = v[s] < NV;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) w[s][j] = ok ? Wt[j * NV + v[s]] : 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) vt[s][c] = ok ? vtemp[v[s] * 3 + c] : 0.f;
-    }
-    const float4* A4 = reinterpret_cast<const float4*>(A) + (size_t)h0 * 48;
-    for (int i = tid; i < nh * 48; i += SK_THREADS) sA[i / 48][i % 48] = A4[i];
-    __syncthreads();
-    for (int hh = 0; hh < nh; ++hh) {
-        const size_t h = h0 + hh;
-        float vp[SK_SLOTS][3], T[SK_SLOTS][12];
-#pragma unroll
-        for (int s = 0; s < SK_SLOTS; ++s) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) vp[s][c] = (v[s] < NV) ? vt[s][c] + off[h * LDN + v[s] * 3 + c] : 0.f;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) T[s][i] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            float4 r0 = sA[hh][j * 3 + 0], r1 = sA[hh][j * 3 + 1], r2 = sA[hh][j * 3 + 2];
-#pragma unroll
-            for (int s = 0; s < SK_SLOTS; ++s) {
-                const float ww = w[s][j];
-                T[s][0] += ww * r0.x; T[s][1] += ww * r0.y; T[s][2] += ww * r0.z; T[s][3] += ww * r0.w;
-                T[s][4] += ww * r1.x; T[s][5] += ww * r1.y; T[s][6] += ww * r1.z; T[s][7] += ww * r1.w;
-                T[s][8] += ww * r2.x; T[s][9] += ww * r2.y; T[s][10] += ww * r2.z; T[s][11] += ww * r2.w;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < SK_SLOTS; ++s) {
-            if (v[s] < NV) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-                    verts[(h * NV + v[s]) * 3 + r] =
-                        T[s][r * 4 + 0] * vp[s][0] + T[s][r * 4 + 1] * vp[s][1] + T[s][r * 4 + 2] * vp[s][2] + T[s][r * 4 + 3];
-            }
-        }
-    }
-}
 
 // Reduce-scatter of 48 per-lane partial sums over the 32 lanes of a warp (fixed order).
 // Afterwards acc[0..2] of every lane holds the warp totals of elements seg..seg+2 where
@@ -1195,21 +1138,12 @@ int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const f
 
 int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
-    // the tensor-core version is the product path; IHMR_B200_SKIN_SIMT=1 selects the FP32-pipe kernel it replaced
-    const char* simt = getenv("IHMR_B200_SKIN_SIMT");
-    if (!(simt && simt[0] == '1')) return launch_skin_fwd_tc(m, n, off, A, verts, st);
-    k_skin_fwd<<<(n + SK_HPC - 1) / SK_HPC, SK_THREADS, 0, st>>>(n, off, A, m->vtemp, m->Wt, verts);
-    IHMR_LAUNCH_OK();
-    return IHMR_OK;
+    return launch_skin_fwd_tc(m, n, off, A, verts, st);      // the blend T = W . A^T runs on tcgen05 (blend_tc.cu)
 }
 
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
                     const float* gtips, float* gposed, float* dA, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
-    // IHMR_B200_SKIN_BWD_TC=1 selects the tensor-core pair of blend_tc.cu (correct, but measured slower than this
-    // FP32-pipe kernel: 4.9 vs 3.0 ms at 131072 hands)
-    const char* tc = getenv("IHMR_B200_SKIN_BWD_TC");
-    if (tc && tc[0] == '1') return launch_skin_bwd_tc(m, n, off, A, gverts, gtips, gposed, dA, st);
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_skin_bwd, SKIN_BWD_SMEM, configured)) return rc;
     k_skin_bwd<<<(n + SK_HPC - 1) / SK_HPC, SKB_THREADS, SKIN_BWD_SMEM, st>>>(n, off, A, m->vtemp, m->W4,

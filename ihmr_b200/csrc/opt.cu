@@ -3,8 +3,6 @@
 // snapshot selection and the optimiser step.
 #include <math.h>
 
-#include <cstdlib>
-
 #include "kernels.cuh"
 
 namespace ihmr {
@@ -55,6 +53,44 @@ __device__ __forceinline__ float block64_sum(float v, float* red) {
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     return red[0] + red[1];
+}
+
+// Online form of filter_by_losses + select_params (src/utils/opt_utils.py:104-152) for one frame and one
+// snapshot: crit = this snapshot's [joints_3d_loss_p, collision_loss, joints_2d_loss_p]; org = the same at snapshot 0;
+// best = the best selected criterion so far.  Returns true when the snapshot becomes the frame's choice.
+//   valid  <=> crit[f] <= org[f] * (1 + (percent + 0.1) / 100) for every filter f      (:111-113, '<=' at :131)
+//   score   =  valid ? crit[select] : 1e11                                             (:134-139)
+//   snapshot 0 is always eligible with its true score (:140); argmin keeps the FIRST minimum (:146), hence '<'.
+__device__ __forceinline__ bool snapshot_decide(bool first, const float* crit, float* org, float* best, int n_filters,
+                                                const int* filter_loss, const float* filter_factor, int select_loss) {
+    if (first) {
+        org[0] = crit[0]; org[1] = crit[1]; org[2] = crit[2];
+        *best = crit[select_loss];
+        return true;
+    }
+    bool ok = true;
+    for (int f = 0; f < n_filters; ++f) ok = ok && (crit[filter_loss[f]] <= org[filter_loss[f]] * filter_factor[f]);
+    const float score = ok ? crit[select_loss] : 100000000000.0f;
+    const bool better = score < *best;
+    if (better) *best = score;
+    return better;
+}
+
+// test / tooling entry: the selection alone over stacked per-snapshot criteria (S,B,3) -> chosen snapshot index (B)
+__global__ void k_select_snapshots(int S, int B, const float* __restrict__ crit, int n_filters, int f0, int f1, int f2, int f3,
+                                   float p0, float p1, float p2, float p3, int select_loss, int* __restrict__ index) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int fl[4] = {f0, f1, f2, f3};
+    const float ff[4] = {p0, p1, p2, p3};
+    float org[3], best = 0.f;
+    int pick = 0;
+    for (int sidx = 0; sidx < S; ++sidx) {
+        const float* c = crit + ((size_t)sidx * B + b) * 3;
+        const float cc[3] = {c[0], c[1], c[2]};
+        if (snapshot_decide(sidx == 0, cc, org, &best, n_filters, fl, ff, select_loss)) pick = sidx;
+    }
+    index[b] = pick;
 }
 
 __global__ void __launch_bounds__(FL_THREADS) k_frame_loss(FrameLossArgs a) {
@@ -252,21 +288,8 @@ __global__ void __launch_bounds__(FL_THREADS) k_frame_loss(FrameLossArgs a) {
         }
         if (a.snap_mode) {
             const float crit[3] = {j3d_b, col, j2d_b};
-            float* org = a.origin + (size_t)b * 3;
-            if (a.snap_mode == 1) {
-                org[0] = crit[0]; org[1] = crit[1]; org[2] = crit[2];
-                a.best[b] = crit[a.select_loss];
-                a.take[b] = 1;
-            } else {
-                bool ok = true;
-                for (int f = 0; f < a.n_filters; ++f)
-                    ok = ok && (crit[a.filter_loss[f]] <= org[a.filter_loss[f]] * a.filter_factor[f]);
-                // invalid snapshots score 1e11 in the reference (opt_utils.py:134-139)
-                const float score = ok ? crit[a.select_loss] : 100000000000.0f;
-                const bool better = score < a.best[b];      // strict: first minimum wins (argmin)
-                if (better) a.best[b] = score;
-                a.take[b] = better ? 1 : 0;
-            }
+            a.take[b] = snapshot_decide(a.snap_mode == 1, crit, a.origin + (size_t)b * 3, a.best + b, a.n_filters,
+                                        a.filter_loss, a.filter_factor, a.select_loss) ? 1 : 0;
         }
     }
 }
@@ -361,6 +384,19 @@ __global__ void k_export_verts(int B, const float* verts, const float* joints16,
     l[0] = -vl[0] + (prm[P_TRANS + 0] + (jr[0] + jl[0]));
     l[1] = vl[1] + (prm[P_TRANS + 1] + (jr[1] - jl[1]));
     l[2] = vl[2] + (prm[P_TRANS + 2] + (jr[2] - jl[2]));
+}
+
+// percent = (float(criterion) + 0.1) / 100 ; bar = origin * (1 + percent)   (opt_utils.py:111-112)
+static inline float filter_factor_of(float percent) { return (float)(1.0 + ((double)percent + 0.1) / 100.0); }
+
+int select_snapshots(int S, int B, const float* crit, const ihmr_stage_t* stg, int* index, cudaStream_t st) {
+    float ff[4] = {1.f, 1.f, 1.f, 1.f};
+    int fl[4] = {0, 0, 0, 0};
+    for (int f = 0; f < stg->n_filters; ++f) { ff[f] = filter_factor_of(stg->filter_percent[f]); fl[f] = stg->filter_loss[f]; }
+    k_select_snapshots<<<(B + 127) / 128, 128, 0, st>>>(S, B, crit, stg->n_filters, fl[0], fl[1], fl[2], fl[3], ff[0], ff[1], ff[2], ff[3],
+                                                         stg->select_loss, index);
+    IHMR_LAUNCH_OK();
+    return IHMR_OK;
 }
 
 // ---------------------------------------------------------------------------- host driver
@@ -471,7 +507,7 @@ struct IterPlan {
                               // 2 = later iterations (affine in beta); backward is the affine one in both
 };
 
-static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
+static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot, bool generic) {
     const bool live_blend = mask & (IHMR_P_R_POSE | IHMR_P_L_POSE | IHMR_P_R_SHAPE | IHMR_P_L_SHAPE);
     const bool live_mano = live_blend || (mask & (IHMR_P_R_ORIENT | IHMR_P_L_ORIENT));
     IterPlan p;
@@ -480,10 +516,7 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot) {
     p.mano_bwd = live_mano;
     p.blend_bwd = live_blend;
     p.sdf_skip_grid = (!live_mano && !snapshot) ? 2 : 0;
-    // IHMR_B200_GENERIC_STAGES=1 keeps every stage on the generic kernel chain (used by the tests that
-    // check the stage-specialised paths against it)
-    const char* generic = getenv("IHMR_B200_GENERIC_STAGES");
-    if (generic && generic[0] == '1') return p;
+    if (generic) return p;      // IHMR_STAGE_GENERIC_KERNELS: every stage on the generic kernel chain
     if ((mask & (IHMR_P_R_SHAPE | IHMR_P_L_SHAPE)) &&
         !(mask & (IHMR_P_R_POSE | IHMR_P_L_POSE | IHMR_P_R_ORIENT | IHMR_P_L_ORIENT))) {   // opt_default stage 3
         p.shape = first ? 1 : 2;
@@ -562,14 +595,13 @@ int opt_stage(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr
             la.n_filters = stg->n_filters;
             for (int f = 0; f < stg->n_filters; ++f) {
                 la.filter_loss[f] = stg->filter_loss[f];
-                // percent = (float(criterion) + 0.1) / 100 ; bar = origin * (1 + percent)   (opt_utils.py:111-112)
-                la.filter_factor[f] = (float)(1.0 + ((double)stg->filter_percent[f] + 0.1) / 100.0);
+                la.filter_factor[f] = filter_factor_of(stg->filter_percent[f]);
             }
             la.select_loss = stg->select_loss;
             la.origin = w.origin; la.best = w.best; la.take = w.take;
             ++snaps;
         }
-        int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, j == 0, snap), true);
+        int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, j == 0, snap, stg->flags & IHMR_STAGE_GENERIC_KERNELS), true);
         if (rc) return rc;
         StepArgs sa{};
         sa.B = B; sa.mask = stg->update_mask; sa.optimizer = optimizer; sa.lr = stg->lr;
@@ -599,9 +631,9 @@ int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params
     FrameLossArgs la = base_loss_args(B, bs_norm, params, tg, stg, w);
     // one untimed full iteration fills every cached buffer, then the steady-state iteration is timed
     IHMR_CUDA_OK(cudaMemsetAsync(w.sdf_hints, 0, sdf_hint_bytes(B), st));
-    int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, true, true), true);
+    int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, true, true, stg->flags & IHMR_STAGE_GENERIC_KERNELS), true);
     if (rc) return rc;
-    rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, &prof, plan_iteration(stg->update_mask, false, false), true);
+    rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, &prof, plan_iteration(stg->update_mask, false, false, stg->flags & IHMR_STAGE_GENERIC_KERNELS), true);
     if (rc) return rc;
     StepArgs sa{};
     sa.B = B; sa.mask = stg->update_mask; sa.optimizer = IHMR_OPT_ADAM; sa.lr = 0.f;   // lr 0: parameters unchanged

@@ -25,6 +25,70 @@ from .mano_layer import create as create_mano
 from .mano_layer import _ptr, _stream
 from .strategies import strategies
 
+INPUT_KEYS = ("hand_type_array", "hand_type_valid", "joints_2d", "joints_3d", "hand_trans", "mano_pose", "mano_betas",
+              "mano_params_weight", "init_cam", "init_pose_params", "init_shape_params", "init_hand_trans",
+              "init_joints_2d", "init_joints_3d", "init_hand_trans_j")     # opt_dataset.py:176-196 (tensor entries)
+
+
+class _PinnedBuffer:
+    """One pinned staging tensor exported to numpy through the array interface, so that numpy keeps a reference
+    to THIS object (as the base of the array and of every view of it) for as long as the data is in use."""
+    _TYPESTR = {torch.float32: "<f4", torch.int32: "<i4"}
+
+    def __init__(self, shape, dtype):
+        self.tensor = torch.empty(shape, dtype=dtype, pin_memory=True)
+        self.__array_interface__ = {"data": (self.tensor.data_ptr(), False), "shape": tuple(shape),
+                                    "typestr": self._TYPESTR[dtype], "version": 3}
+
+    def array(self) -> np.ndarray:
+        return np.asarray(self)
+
+
+class _PinnedPool:
+    """Pinned host staging buffers for get_pred_result.  A buffer is handed out again only when nothing outside
+    the pool references it any more: the numpy arrays returned to the caller (and every view of them, e.g. the
+    per-sample rows src/utils/evaluator.py:74-86 keeps) keep their buffer referenced, so results stay valid
+    for as long as the caller holds them."""
+
+    def __init__(self):
+        self._bufs = []
+
+    def get(self, shape, dtype) -> _PinnedBuffer:
+        shape = tuple(shape)
+        for b in self._bufs:
+            # references when free: the list, the loop variable, getrefcount's argument
+            if tuple(b.tensor.shape) == shape and b.tensor.dtype == dtype and sys.getrefcount(b) <= 3:
+                return b
+        b = _PinnedBuffer(shape, dtype)
+        self._bufs.append(b)
+        return b
+
+    def trim(self):
+        """Drops the buffers nobody holds (frees their pinned memory)."""
+        self._bufs = [b for b in self._bufs if sys.getrefcount(b) > 3]
+
+
+class PrefetchedInput:
+    """Device copies of one batch issued on the H2D stream (OptimizeModel.prefetch_input)."""
+
+    def __init__(self, tensors, event):
+        self.tensors, self.event = tensors, event
+
+
+class PendingResult:
+    """Result of get_pred_result_async: the D2H copies are in flight on the D2H stream."""
+
+    def __init__(self, arrays, event, keep):
+        self._arrays, self._event, self._keep = arrays, event, keep
+
+    def wait(self):
+        """Blocks until THIS batch's copies are done (not the device) and returns the 13 arrays."""
+        if self._event is not None:
+            self._event.synchronize()
+            self._event, self._keep = None, None
+        return self._arrays
+
+
 DEFAULT_LOSS_WEIGHTS = dict(joints_2d_loss=10.0, joints_3d_loss=1000.0, trans_loss_weight=100.0,
                             shape_reg_loss_weight=0.1, collision_loss_weight=1.0,
                             finger_reg_loss_weight=100000.0)   # optimize_model.py:84-92
@@ -71,7 +135,10 @@ class OptimizeModel:
         assert abs(self.default_loss_weights["collision_loss_weight"] - 1.0) < 1e-7
         self._ws = None
         self._buf: Dict[str, torch.Tensor] = {}
-        self._pinned: Dict[str, torch.Tensor] = {}
+        self._pinned = _PinnedPool()
+        self._h2d_stream = torch.cuda.Stream(self.device)
+        self._d2h_stream = torch.cuda.Stream(self.device)
+        self._d2h_done = None        # event of the last result copy: the next final forward must not overtake it
 
     def _build_device_model(self):
         from .mano_layer import DeviceModel
@@ -81,29 +148,39 @@ class OptimizeModel:
         return DeviceModel(arrays, right.faces, left.faces, self.device.index or 0)
 
     # -------------------------------------------------------------------------- input
-    def set_input(self, input):
-        """H2D copy of one batch (keys of src/data/opt_dataset.py:176-196)."""
+    def prefetch_input(self, input) -> PrefetchedInput:
+        """Starts the H2D copy of a batch on the model's copy stream and returns at once; pass the handle to
+        set_input later.  With pinned source tensors the copy overlaps whatever the compute stream is doing."""
         dev = self.device
+        out = {}
+        with torch.cuda.stream(self._h2d_stream):
+            for key in INPUT_KEYS:
+                t = input[key]
+                t = t if isinstance(t, torch.Tensor) else torch.as_tensor(t)
+                t = t.to(torch.float32)
+                # pageable source: torch stages it synchronously; pinned sources go straight to the device
+                out[key] = t.to(dev, non_blocking=t.device.type != "cpu" or t.is_pinned()).contiguous()
+            ev = torch.cuda.Event()
+            ev.record(self._h2d_stream)
+        return PrefetchedInput(out, ev)
 
-        def put(key):
-            t = input[key]
-            t = t if isinstance(t, torch.Tensor) else torch.as_tensor(t)
-            t = t.to(torch.float32)
-            if t.device.type == "cpu" and not t.is_pinned():
-                # pageable source: one staging copy; pinned sources go straight to the device
-                return t.to(dev, non_blocking=False).contiguous()
-            return t.to(dev, non_blocking=True).contiguous()
-
-        self.hand_type_array = put("hand_type_array")
-        self.hand_type_valid = put("hand_type_valid")
-        self.joints_2d, self.joints_3d = put("joints_2d"), put("joints_3d")
-        self.hand_trans = put("hand_trans")
-        self.gt_pose_params, self.gt_shape_params = put("mano_pose"), put("mano_betas")
-        self.mano_params_weight = put("mano_params_weight")
-        self.init_cam, self.init_pose_params = put("init_cam"), put("init_pose_params")
-        self.init_shape_params, self.init_hand_trans = put("init_shape_params"), put("init_hand_trans")
-        self.init_joints_2d, self.init_joints_3d = put("init_joints_2d"), put("init_joints_3d")
-        self.init_hand_trans_j = put("init_hand_trans_j")
+    def set_input(self, input):
+        """H2D copy of one batch (keys of src/data/opt_dataset.py:176-196), or adoption of a prefetched one."""
+        pre = input if isinstance(input, PrefetchedInput) else self.prefetch_input(input)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(pre.event)
+        t = pre.tensors
+        for v in t.values():
+            v.record_stream(cur)         # allocated on the copy stream, consumed on the compute stream
+        self.hand_type_array, self.hand_type_valid = t["hand_type_array"], t["hand_type_valid"]
+        self.joints_2d, self.joints_3d = t["joints_2d"], t["joints_3d"]
+        self.hand_trans = t["hand_trans"]
+        self.gt_pose_params, self.gt_shape_params = t["mano_pose"], t["mano_betas"]
+        self.mano_params_weight = t["mano_params_weight"]
+        self.init_cam, self.init_pose_params = t["init_cam"], t["init_pose_params"]
+        self.init_shape_params, self.init_hand_trans = t["init_shape_params"], t["init_hand_trans"]
+        self.init_joints_2d, self.init_joints_3d = t["init_joints_2d"], t["init_joints_3d"]
+        self.init_hand_trans_j = t["init_hand_trans_j"]
         B = self.init_cam.shape[0]
         assert B == self.batch_size, "batch rows must equal opt.batchSize (optimize_model.py:185)"
         assert self.init_joints_2d.shape == (B, 42, 3) and self.init_joints_3d.shape == (B, 42, 4)
@@ -157,6 +234,9 @@ class OptimizeModel:
         """Final-style forward: fills pred_*_hand_verts, pred_joints_3d (root aligned, as the
         reference leaves it after __compute_loss), collision outputs."""
         B, ws = self.batch_size, self._workspace()
+        if self._d2h_done is not None:       # the previous batch's result copy reads the buffers written below
+            torch.cuda.current_stream(self.device).wait_event(self._d2h_done)
+            self._d2h_done = None
         self.pred_right_hand_verts = self._out("rv", B, 778, 3)
         self.pred_left_hand_verts = self._out("lv", B, 778, 3)
         self.pred_joints_3d = self._out("j3d", B, 42, 3)
@@ -190,32 +270,65 @@ class OptimizeModel:
         return losses, grad
 
     # ------------------------------------------------------------------------- output
-    def _to_host(self, name: str, t: torch.Tensor) -> np.ndarray:
-        """D2H through a cached pinned staging buffer (async on the current stream)."""
-        t = t.detach().contiguous()
-        buf = self._pinned.get(name)
-        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            self._pinned[name] = buf
-        buf.copy_(t, non_blocking=True)
-        return buf.numpy()
+    def get_pred_result_async(self) -> PendingResult:
+        """Starts the D2H copies of the 13 result arrays (optimize_model.py:418-435) on the model's copy stream,
+        ordered after everything enqueued so far on the current stream, and returns without waiting."""
+        B = self.batch_size
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        src = OrderedDict(
+            pred_cam_params=self.pred_cam_params, pred_hand_trans=self.pred_hand_trans,
+            pred_shape_params=self.pred_shape_params, pred_pose_params=self.pred_pose_params,
+            pred_right_hand_verts=self.pred_right_hand_verts, pred_left_hand_verts=self.pred_left_hand_verts,
+            mano_params_weight=self.mano_params_weight, pred_joints_3d=self.pred_joints_3d,
+            gt_joints_3d=self.joints_3d, collision_loss=self.collision_loss_batch,
+            collision_loss_origin_scale=self.collision_loss_origin_scale)
+        res, keep = OrderedDict(), []
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(ready)
+            for name, t in src.items():
+                t = t.detach()
+                buf = self._pinned.get(t.shape, t.dtype)
+                buf.tensor.copy_(t, non_blocking=True)     # strided views (parameter columns) are gathered by the copy
+                t.record_stream(self._d2h_stream)
+                keep.append(t)
+                res[name] = buf.array()
+                del buf
+            done = torch.cuda.Event()
+            done.record(self._d2h_stream)
+        res["do_flip"] = np.zeros(B).astype(np.int32)
+        res["pred_hand_type"] = np.ones(B).astype(np.int32)
+        self._d2h_done = done
+        return PendingResult(res, done, keep)
 
     def get_pred_result(self):
-        """optimize_model.py:418-435: the 13 numpy arrays the evaluator consumes. The arrays
-        are views of pinned staging buffers and stay valid until the next call."""
-        B = self.batch_size
-        c = self._to_host
-        res = OrderedDict(
-            pred_cam_params=c("cam", self.pred_cam_params), pred_hand_trans=c("trans", self.pred_hand_trans),
-            pred_shape_params=c("shape", self.pred_shape_params), pred_pose_params=c("pose", self.pred_pose_params),
-            pred_right_hand_verts=c("rv", self.pred_right_hand_verts),
-            pred_left_hand_verts=c("lv", self.pred_left_hand_verts),
-            mano_params_weight=c("mpw", self.mano_params_weight), pred_joints_3d=c("j3d", self.pred_joints_3d),
-            gt_joints_3d=c("gtj3d", self.joints_3d), collision_loss=c("col", self.collision_loss_batch),
-            collision_loss_origin_scale=c("ori", self.collision_loss_origin_scale),
-            do_flip=np.zeros(B).astype(np.int32), pred_hand_type=np.ones(B).astype(np.int32))
-        torch.cuda.current_stream(self.device).synchronize()     # the one sync of the batch
-        return res
+        """optimize_model.py:418-435: the 13 numpy arrays the evaluator consumes.  The arrays own their (pinned)
+        memory: they stay valid after later calls, as the reference's freshly allocated arrays do.  Waits for this
+        batch's copies only."""
+        return self.get_pred_result_async().wait()
+
+    def run_pipelined(self, batches, iter_id=0, num_iter=1):
+        """Generator over an iterable of input dicts (the reference's per-batch loop, src/optimize.py:61-73, with
+        the copies taken off the critical path): yields each batch's result dict in order.  While batch k
+        refines, batch k+1 is copied to the device and batch k-1's results are copied back, on separate
+        streams; the host runs at most one batch ahead of the results it hands out."""
+        it = iter(batches)
+        first = next(it, None)
+        nxt = self.prefetch_input(first) if first is not None else None
+        pending = None
+        while nxt is not None:
+            self.set_input(nxt)
+            self.init_optimize()
+            self.optimize(iter_id, num_iter)
+            res = self.get_pred_result_async()
+            upcoming = next(it, None)
+            nxt = self.prefetch_input(upcoming) if upcoming is not None else None
+            if pending is not None:
+                yield pending.wait()
+            pending = res
+        if pending is not None:
+            yield pending.wait()
 
     def profile_iteration(self, stage: dict):
         """Device milliseconds of each kernel class for one iteration of `stage` (measurement aid)."""

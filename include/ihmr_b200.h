@@ -128,6 +128,9 @@ enum { IHMR_P_CAM = 1, IHMR_P_TRANS = 2, IHMR_P_R_ORIENT = 4, IHMR_P_R_POSE = 8,
        IHMR_P_L_POSE = 32, IHMR_P_R_SHAPE = 64, IHMR_P_L_SHAPE = 128 };
 enum { IHMR_LOSS_JOINTS_3D_P = 0, IHMR_LOSS_COLLISION = 1, IHMR_LOSS_JOINTS_2D_P = 2 };
 enum { IHMR_OPT_ADAM = 0, IHMR_OPT_SGD = 1 };
+/* IHMR_STAGE_GENERIC_KERNELS: run this stage on the generic kernel chain even where a specialised rewrite
+ * exists (orientation-only and shape-only stages); the tests compare the two. */
+enum { IHMR_STAGE_GENERIC_KERNELS = 1 };
 
 typedef struct {
     uint32_t update_mask;   /* OR of IHMR_P_*: stage['update_params'] */
@@ -138,6 +141,7 @@ typedef struct {
     int32_t filter_loss[4]; /* IHMR_LOSS_* */
     float filter_percent[4];/* '+0' -> 0, '-10' -> -10 */
     int32_t select_loss;    /* IHMR_LOSS_* */
+    uint32_t flags;         /* OR of IHMR_STAGE_* */
 } ihmr_stage_t;
 
 /* Per-batch device inputs of the loop (what set_input copies, optimize_model.py:120-168). */
@@ -153,8 +157,8 @@ typedef struct {
  * optimiser state, and the per-vertex transform cache of the shape-only stages. */
 size_t ihmr_opt_workspace_bytes(int n_frames);
 /* Stages that update only the global orientations or only the shape coefficients run on specialised
- * kernels (rigid / affine rewrites of the same layer, equal to rounding); the environment variable
- * IHMR_B200_GENERIC_STAGES=1 keeps every stage on the generic kernel chain (tests compare the two).
+ * kernels (rigid / affine rewrites of the same layer, equal to rounding) unless the stage carries
+ * IHMR_STAGE_GENERIC_KERNELS.
  * params (B,122) is read and updated in place; bs_norm is the batch size every batch-mean loss
  * divides by (the reference's opt.batchSize), independent of how frames are sharded. */
 int ihmr_opt_stage(const ihmr_model_t* model, int n_frames, int bs_norm, float* params,
@@ -176,6 +180,13 @@ int ihmr_opt_value_and_grad(const ihmr_model_t* model, int n_frames, int bs_norm
                             float* grad, void* workspace, size_t workspace_bytes,
                             ihmr_stream_t stream);
 
+/* The stage-end selection on its own (a13): `filter_by_losses` + `select_params`
+ * (src/utils/opt_utils.py:104-152) over stacked per-snapshot criteria (S,B,3) =
+ * [joints_3d_loss_p, collision_loss, joints_2d_loss_p] -> index (B) of the chosen snapshot.  It runs the same
+ * device routine ihmr_opt_stage applies online after every snapshot; filter / select fields of `stage` are used. */
+int ihmr_select_snapshots(int n_snapshots, int n_frames, const float* criteria, const ihmr_stage_t* stage,
+                          int32_t* index, ihmr_stream_t stream);
+
 /* ---- evaluator metrics on the device ------------------------------
  * Replaces the host-side per-frame metric code the reference runs after get_pred_result:
  * mu.get_single_joints_error and mu.get_single_pa_inter_joints_error(use_rot=False)
@@ -196,6 +207,11 @@ int ihmr_opt_profile_iteration(const ihmr_model_t* model, int n_frames, int bs_n
                                const ihmr_targets_t* targets, const ihmr_stage_t* stage,
                                float* ms_per_kernel, void* workspace, size_t workspace_bytes,
                                ihmr_stream_t stream);
+
+/* Measurement aid (synchronises `stream`): FP32 FMA throughput of the model's device in TFLOP/s from an
+ * FFMA-only micro-kernel — the denominator for the FP32-pipe fraction SURVEY.md §8(d) asks for next to GB/s
+ * (MEASURED_PEAKS.json has no FP32 figure).  tflops: HOST float; scratch: >= 4 bytes of device memory. */
+int ihmr_measure_fp32_peak(const ihmr_model_t* model, float* tflops, void* scratch, ihmr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,7 @@ def test_version_and_error_conventions(lib):
 def test_stage_struct_matches_header_and_strategy_dicts():
     from ihmr_b200 import _lib
     from ihmr_b200.strategies import opt_default, strategies
-    assert ctypes.sizeof(_lib.Stage) == 4 * (3 + 6 + 1 + 4 + 4 + 1)
+    assert ctypes.sizeof(_lib.Stage) == 4 * (3 + 6 + 1 + 4 + 4 + 1 + 1)
     assert ctypes.sizeof(_lib.Targets) == 5 * ctypes.sizeof(ctypes.c_void_p)
     st = _lib.make_stage(opt_default[2])
     assert st.update_mask == (_lib.P_L_POSE | _lib.P_R_POSE) and st.epoch == 300

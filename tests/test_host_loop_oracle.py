@@ -90,3 +90,35 @@ def test_filter_thresholds_and_first_minimum():
     col = t([[0.0], [0.0]])
     assert _select(j3d, col, params[:2, :1]) == [0]          # valid but not better than snapshot 0
     assert HL.INVALID_CRITERIA == ("joints_3d_loss", "joints_2d_loss", "hand_trans_loss")
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present (GPU box)")
+def test_unmodified_reference_class_binds_to_the_cuda_leaves(model_root, oracle_layers, monkeypatch):
+    """Boundary L0 under the reference's OWN class: /root/reference/src/models/optimize_model.py,
+    unmodified, with sys.modules['smplx'] / ['sdf'] set to the ihmr_b200 leaf modules.  This container has the
+    reference but no GPU, and the GPU box has no reference, so the two can never compute together; what is checked
+    here is everything up to the first kernel: the constructor path (smplx.create signature, the in-place
+    `.shapedirs` edit of optimize_model.py:109-113, `.faces`, `SDFLoss(faces_right, faces_left, robustifier=None)`,
+    `.cuda()`), set_input / init_optimize, and that forward() reaches OUR leaf, which refuses to run on a CPU tensor
+    (no fallback) instead of silently computing something else."""
+    import sys
+
+    import ihmr_b200.mano_layer as mano_layer
+    import ihmr_b200.sdf_loss as sdf_loss
+    from ihmr_b200 import _lib
+    ref_shims._install_shims()                       # ry_utils / opendr stand-ins, .cuda() -> identity on this CPU box
+    monkeypatch.setitem(sys.modules, "smplx", mano_layer)
+    monkeypatch.setitem(sys.modules, "sdf", sdf_loss)
+    for name in [n for n in sys.modules if n == "models" or n.startswith("models.")]:
+        monkeypatch.delitem(sys.modules, name)       # re-import the reference modules against the new leaves
+    monkeypatch.syspath_prepend(ref_shims.REFERENCE_SRC)
+    from models.optimize_model import OptimizeModel  # the reference's file, unmodified
+    B = 2
+    model = OptimizeModel(ref_shims.make_opt(model_root, B, save_mid_freq=1))
+    assert isinstance(model.mano_models["right"], mano_layer.ManoLayer)
+    assert isinstance(model.loss_util.sdf_loss, sdf_loss.SDFLoss) if hasattr(model, "loss_util") else True
+    assert model.mano_models["left"].faces.shape == (1538, 3)
+    model.set_input(H.torch_batch(H.make_batch(oracle_layers[0], 0, B)))
+    model.init_optimize()
+    with pytest.raises(_lib.IhmrError, match="no CPU path"):
+        model.forward()

@@ -84,6 +84,7 @@ def main():
     ap.add_argument("--frames", type=int, default=8192)
     ap.add_argument("--mode", default="typical")
     ap.add_argument("--stats", action="store_true")
+    ap.add_argument("--stats-json", action="store_true", help="work counters as one JSON line (tests)")
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--start", type=int, default=0)
@@ -110,6 +111,18 @@ def main():
                 break
             t = op.time(hv[:b].contiguous())
             print(json.dumps({"what": "sweep", "mode": args.mode, "frames": b, "ms": t, "us_per_frame": t * 1e3 / b}), flush=True)
+
+    if args.stats_json:
+        stats = torch.zeros(B, 32, dtype=torch.int32, device=dev)
+        op.run(hv, stats=stats)
+        torch.cuda.synchronize()
+        st = stats.cpu().numpy().astype(np.int64)
+        searching = (st[:, 0] > 0).astype(np.int64) + (st[:, 2] > 0)
+        print(json.dumps({"what": "stats", "frames": B, "voxels": int(st[:, 0].sum() + st[:, 2].sum()), "passes": int(st[:, 10].sum()),
+                          "max_passes_per_direction": int(np.max(st[:, 10] - np.maximum(searching - 1, 0))) if B else 0,
+                          "rounds": int(st[:, 1].sum() + st[:, 3].sum()), "candidates": int(st[:, 7].sum()),
+                          "rays_in_place": int(st[:, 11].sum()), "candidates_in_place": int(st[:, 12].sum()),
+                          "prep_done_directions": int(st[:, 16].sum() + st[:, 17].sum())}), flush=True)
 
     if args.stats:
         stats = torch.zeros(B, 32, dtype=torch.int32, device=dev)
