@@ -139,6 +139,13 @@ class OptimizeModel:
         self._h2d_stream = torch.cuda.Stream(self.device)
         self._d2h_stream = torch.cuda.Stream(self.device)
         self._d2h_done = None        # event of the last result copy: the next final forward must not overtake it
+        self._d2h_small = None       # event after its first part (parameters, pass-through inputs): next set_input / init
+        self._dev_in: Dict[str, torch.Tensor] = {}
+        self.params = None
+        # CUDA graphs of the stage calls (launch-bound at small batches: ~2000 launches per step)
+        self.use_cuda_graphs = bool(getattr(opt, "use_cuda_graphs", True))
+        self._graphs: Dict[tuple, tuple] = {}
+        self.replayed_launches = 0   # kernels launched through graph replays (ihmr_launch_count only sees direct launches)
 
     def _build_device_model(self):
         from .mano_layer import DeviceModel
@@ -169,9 +176,20 @@ class OptimizeModel:
         pre = input if isinstance(input, PrefetchedInput) else self.prefetch_input(input)
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(pre.event)
-        t = pre.tensors
-        for v in t.values():
+        if self._d2h_small is not None:      # the previous batch's result copy still reads gt_joints_3d / mano_params_weight
+            cur.wait_event(self._d2h_small)
+        # The batch lives in persistent device buffers (same addresses for every batch, so captured CUDA graphs of the
+        # stages stay valid); the prefetched copy is moved in with device-to-device copies on the compute stream.
+        t = {}
+        for key, v in pre.tensors.items():
+            buf = self._dev_in.get(key)
+            if buf is None or buf.shape != v.shape:
+                buf = torch.empty_like(v)
+                self._dev_in[key] = buf
+                self._graphs.clear()
+            buf.copy_(v, non_blocking=True)
             v.record_stream(cur)         # allocated on the copy stream, consumed on the compute stream
+            t[key] = buf
         self.hand_type_array, self.hand_type_valid = t["hand_type_array"], t["hand_type_valid"]
         self.joints_2d, self.joints_3d = t["joints_2d"], t["joints_3d"]
         self.hand_trans = t["hand_trans"]
@@ -192,9 +210,17 @@ class OptimizeModel:
     def init_optimize(self):
         """optimize_model.py:235-251: start from the prior prediction. The seven parameter
         groups live in one (B,122) matrix [cam | trans | pose 96 | shape 20]."""
-        self.params = torch.cat([self.init_cam, self.init_hand_trans[:, 0, :3], self.init_pose_params,
-                                 self.init_shape_params], dim=1).contiguous()
-        assert self.params.shape == (self.batch_size, 122)
+        if self._d2h_small is not None:      # the previous batch's result copy still reads the parameter matrix
+            torch.cuda.current_stream(self.device).wait_event(self._d2h_small)
+            self._d2h_small = None
+        if getattr(self, "params", None) is None or self.params.shape != (self.batch_size, 122):
+            self.params = torch.empty(self.batch_size, 122, device=self.device, dtype=torch.float32)
+            self._graphs.clear()
+        p = self.params
+        p[:, 0:3].copy_(self.init_cam)
+        p[:, 3:6].copy_(self.init_hand_trans[:, 0, :3])
+        p[:, 6:102].copy_(self.init_pose_params)
+        p[:, 102:122].copy_(self.init_shape_params)
 
     # views with the reference's attribute names
     pred_cam_params = property(lambda self: self.params[:, 0:3])
@@ -230,6 +256,34 @@ class OptimizeModel:
                                            C.byref(self._targets), C.byref(st), int(self.opt.save_mid_freq),
                                            optimizer, _ptr(ws), ws.numel(), _stream(self.device)), "ihmr_opt_stage")
 
+    def _replay(self, key, fn):
+        """Runs fn() (stream-ordered C-ABI launches only, no allocation) directly the first time and through a CUDA
+        graph captured right after it from then on.  `key` must change whenever a pointer or argument of fn does."""
+        if not self.use_cuda_graphs:
+            fn()
+            return
+        hit = self._graphs.get(key)
+        if hit is not None:
+            hit[0].replay()
+            self.replayed_launches += hit[1]
+            return
+        fn()                                  # this batch: direct launches (also does the one-time kernel attribute setup)
+        g = torch.cuda.CUDAGraph()
+        n0 = self.lib.ihmr_launch_count()
+        with torch.cuda.graph(g, stream=self._capture_stream()):
+            fn()                              # recorded, not executed
+        self._graphs[key] = (g, int(self.lib.ihmr_launch_count() - n0))
+
+    def _capture_stream(self):
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(self.device)
+        return self._cap_stream
+
+    def _graph_key(self, tag, stage=None):
+        ptrs = (self.params.data_ptr(), self._workspace().data_ptr()) + tuple(t.data_ptr() for t in self._dev_in.values())
+        extra = bytes(_lib.make_stage(stage)) if stage is not None else b""
+        return (tag, self.batch_size, self.bs_norm, int(self.opt.save_mid_freq), getattr(self.opt, "optimizer", "adam"), ptrs, extra)
+
     def forward(self):
         """Final-style forward: fills pred_*_hand_verts, pred_joints_3d (root aligned, as the
         reference leaves it after __compute_loss), collision outputs."""
@@ -243,15 +297,18 @@ class OptimizeModel:
         self.collision_loss_batch = self._out("col", B)
         self.collision_loss_origin_scale = self._out("ori", B, 1556)
         self.joints_3d_loss_p_batch = self._out("j3dp", B)
-        _lib.check(self.lib.ihmr_opt_final(self._model.handle, B, _ptr(self.params), C.byref(self._targets),
-                                           _ptr(self.pred_right_hand_verts), _ptr(self.pred_left_hand_verts),
-                                           _ptr(self.pred_joints_3d), _ptr(self.collision_loss_batch),
-                                           _ptr(self.collision_loss_origin_scale), _ptr(self.joints_3d_loss_p_batch),
-                                           _ptr(ws), ws.numel(), _stream(self.device)), "ihmr_opt_final")
+
+        def launch():
+            _lib.check(self.lib.ihmr_opt_final(self._model.handle, B, _ptr(self.params), C.byref(self._targets),
+                                               _ptr(self.pred_right_hand_verts), _ptr(self.pred_left_hand_verts),
+                                               _ptr(self.pred_joints_3d), _ptr(self.collision_loss_batch),
+                                               _ptr(self.collision_loss_origin_scale), _ptr(self.joints_3d_loss_p_batch),
+                                               _ptr(ws), ws.numel(), _stream(self.device)), "ihmr_opt_final")
+        self._replay(self._graph_key("final") + (self.pred_right_hand_verts.data_ptr(), self.collision_loss_origin_scale.data_ptr()), launch)
 
     def optimize(self, iter_id=0, num_iter=1):
         for stage_id, stage in enumerate(self.strategy):
-            self.run_stage(stage)
+            self._replay(self._graph_key(("stage", stage_id), stage), lambda: self.run_stage(stage))
             if self.process_rank <= 0 and not getattr(self.opt, "quiet", False):
                 print(f"iter:{iter_id + 1:04d}/{num_iter:04d}, stage-{stage_id:02d} completes")
                 sys.stdout.flush()
@@ -285,18 +342,30 @@ class OptimizeModel:
             gt_joints_3d=self.joints_3d, collision_loss=self.collision_loss_batch,
             collision_loss_origin_scale=self.collision_loss_origin_scale)
         res, keep = OrderedDict(), []
+        # what the NEXT batch overwrites first (parameter matrix, pass-through inputs) is copied first and gets its own
+        # event; the large arrays are only overwritten by the next batch's final forward
+        early = ("pred_cam_params", "pred_hand_trans", "pred_shape_params", "pred_pose_params", "mano_params_weight", "gt_joints_3d")
+        order = [k for k in src if k in early] + [k for k in src if k not in early]
+        bufs = {}
         with torch.cuda.stream(self._d2h_stream):
             self._d2h_stream.wait_event(ready)
-            for name, t in src.items():
-                t = t.detach()
+            small = None
+            for i, name in enumerate(order):
+                t = src[name].detach()
                 buf = self._pinned.get(t.shape, t.dtype)
                 buf.tensor.copy_(t, non_blocking=True)     # strided views (parameter columns) are gathered by the copy
                 t.record_stream(self._d2h_stream)
                 keep.append(t)
-                res[name] = buf.array()
+                bufs[name] = buf.array()
                 del buf
+                if i == len(early) - 1:
+                    small = torch.cuda.Event()
+                    small.record(self._d2h_stream)
             done = torch.cuda.Event()
             done.record(self._d2h_stream)
+        for name in src:
+            res[name] = bufs[name]
+        self._d2h_small = small
         res["do_flip"] = np.zeros(B).astype(np.int32)
         res["pred_hand_type"] = np.ones(B).astype(np.int32)
         self._d2h_done = done

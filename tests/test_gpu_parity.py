@@ -346,6 +346,31 @@ def test_results_are_owned_and_pipelining_matches(model_root, oracle_layers):
             assert np.array_equal(g[k], ref[k]), k
 
 
+def test_cuda_graph_replay_equals_direct_launches(model_root, oracle_layers):
+    """Stages are replayed from CUDA graphs after the first batch (same kernels, same arguments): bitwise equal."""
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default, with_epochs
+    B = 6
+    batches = [H.torch_batch(H.make_batch(oracle_layers[0], s, B, mode=m)) for s, m in ((0, "typical"), (512, "collision"), (30, "typical"))]
+
+    def run(use_graphs):
+        opt = H.make_opt(model_root, B, save_mid_freq=2, strategy=with_epochs(opt_default, 5), bs_norm=B)
+        opt.use_cuda_graphs = use_graphs
+        m = OptimizeModel(opt)
+        out = []
+        for b in batches:
+            m.set_input(b); m.init_optimize(); m.optimize(0, 1)
+            out.append({k: v.copy() for k, v in m.get_pred_result().items()})
+        return out, m
+
+    direct, _ = run(False)
+    graphed, m = run(True)
+    assert m.replayed_launches > 0 and len(m._graphs) == 5           # 4 stages + the final forward
+    for a, b in zip(direct, graphed):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+
+
 def test_determinism_and_shard_invariance(model_root, oracle_layers):
     from ihmr_b200.optimize_model import OptimizeModel
     from ihmr_b200.strategies import opt_default, with_epochs
