@@ -107,6 +107,21 @@ __device__ __forceinline__ void fetch_chunk(ChunkRegs<NITEMS>& regs, const float
     }
 }
 
+// the same through a row list: rowsrc[i] is the source row of this thread's i-th item (fixed over the chunks), -1 = none
+template <int NITEMS>
+__device__ __forceinline__ void fetch_chunk_rows(ChunkRegs<NITEMS>& regs, const float* __restrict__ src, int ld,
+                                                 const int (&rowsrc)[NITEMS], int k0, int tid) {
+#pragma unroll
+    for (int i = 0; i < NITEMS; ++i) {
+        const int it = tid + i * TC_THREADS;
+        int r, kc;
+        uint32_t off;
+        item_coords(it, r, kc, off);
+        regs.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rowsrc[i] >= 0) regs.v[i] = *reinterpret_cast<const float4*>(src + (size_t)rowsrc[i] * ld + k0 + kc * 4);
+    }
+}
+
 template <int NITEMS>
 __device__ __forceinline__ void store_chunk(const ChunkRegs<NITEMS>& regs, int rows_tile, unsigned char* hi, unsigned char* lo, int tid) {
 #pragma unroll
@@ -122,7 +137,7 @@ __device__ __forceinline__ void store_chunk(const ChunkRegs<NITEMS>& regs, int r
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS)
 k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-              float* __restrict__ C, int ldc) {
+              float* __restrict__ C, int ldc, const int* __restrict__ rows, const int* __restrict__ nrows) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_hi = smem;
     unsigned char* a_lo = a_hi + TC_BM * TC_BK * 4;
@@ -132,6 +147,8 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    if (nrows) M = min(M, *nrows);                        // row list: only its first *nrows entries exist
+    if (m0 >= M) return;
     const int rows_a = min(TC_BM, M - m0);
     const int rows_b = min(BN, Nc - n0);
     const int n_inst = (rows_b + 15) & ~15;               // MMA N: multiple of 16 covering the valid B rows
@@ -153,9 +170,18 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
 
     uint32_t parity = 0;
     const int nchunks = K / TC_BK;
-    ChunkRegs<TC_BM * 8 / TC_THREADS> ra;
+    constexpr int A_ITEMS = TC_BM * 8 / TC_THREADS;
+    ChunkRegs<A_ITEMS> ra;
     ChunkRegs<BN * 8 / TC_THREADS> rb;
-    fetch_chunk(ra, A, lda, m0, rows_a, TC_BM, 0, tid);
+    int rowsrc[A_ITEMS];                                  // source row of this thread's A items (row list or identity)
+#pragma unroll
+    for (int i = 0; i < A_ITEMS; ++i) {
+        int r, kc;
+        uint32_t off;
+        item_coords(tid + i * TC_THREADS, r, kc, off);
+        rowsrc[i] = (r < rows_a) ? (rows ? rows[m0 + r] : m0 + r) : -1;
+    }
+    fetch_chunk_rows(ra, A, lda, rowsrc, 0, tid);
     fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, 0, tid);
     for (int ch = 0; ch < nchunks; ++ch) {
         store_chunk(ra, TC_BM, a_hi, a_lo, tid);
@@ -177,7 +203,7 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
         }
         if (ch + 1 < nchunks) {                                      // next chunk's global loads fly while the MMAs run
-            fetch_chunk(ra, A, lda, m0, rows_a, TC_BM, (ch + 1) * TC_BK, tid);
+            fetch_chunk_rows(ra, A, lda, rowsrc, (ch + 1) * TC_BK, tid);
             fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, (ch + 1) * TC_BK, tid);
         }
         mbar_wait(smem_u32(&mbar), parity);                          // operands may be overwritten, accumulator is current
@@ -213,8 +239,10 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
         for (int i = 0; i < 8; ++i) {
             const int r = (lane >> 3) + 4 * i;               // row inside the quarter's 32 rows
             const int row = m0 + quarter * 32 + r;
-            if (row < M && n0 + c0 + cq < Nc)
-                *reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + c0 + cq) = *reinterpret_cast<const float4*>(stage + r * 36 + cq);
+            if (row < M && n0 + c0 + cq < Nc) {
+                const int drow = rows ? rows[row] : row;
+                *reinterpret_cast<float4*>(C + (size_t)drow * ldc + n0 + c0 + cq) = *reinterpret_cast<const float4*>(stage + r * 36 + cq);
+            }
         }
         __syncwarp();
     }
@@ -398,23 +426,24 @@ int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float
 }
 
 template <int BN>
-static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st) {
+static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st,
+                     const int* rows, const int* nrows) {
     const size_t smem = (size_t)(2 * TC_BM + 2 * BN) * TC_BK * 4;
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_gemm_tf32x3<BN>, smem, configured)) return rc;
     dim3 grid((Nc + BN - 1) / BN, (M + TC_BM - 1) / TC_BM);
-    k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, C, ldc);
+    k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, C, ldc, rows, nrows);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
 
 // C[M,Nc] = A[M,K] . B[Nc,K]^T ; K % 32 == 0, Nc % 4 == 0, lda/ldb/ldc % 4 == 0
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st) {
+                       cudaStream_t st, const int* rows, const int* nrows) {
     if (M <= 0) return IHMR_OK;
     if (K % TC_BK || Nc % 4 || lda % 4 || ldb % 4 || ldc % 4) { set_error("gemm_tf32x3: unsupported shape"); return IHMR_E_INVALID; }
-    if (Nc > 160) return launch_tc<256>(M, Nc, K, A, lda, B, ldb, C, ldc, st);
-    return launch_tc<160>(M, Nc, K, A, lda, B, ldb, C, ldc, st);
+    if (Nc > 160) return launch_tc<256>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows);
+    return launch_tc<160>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows);
 }
 
 }  // namespace ihmr

@@ -40,25 +40,36 @@ int launch_pose_prep(const ihmr_model* m, int n, HandSrc src, float* X, float* A
 int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cudaStream_t st);
 int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts,
                     cudaStream_t st);
-// gverts (n,778,3) may be null; gtips (n,5,3) may be null (extra gradient on the 5 fingertip vertices)
+// Hands whose vertex gradient is identically zero (flagged by the penetration kernels) carry only their five
+// fingertip gradients: the backward kernels take a short path for them and the blend contraction skips them.
+struct SparseGrad {
+    const uint8_t* gzero = nullptr;    // (n) 1 = gverts of this hand are zero and unwritten
+    int* dense_list = nullptr;         // (n) hands with gzero == 0, any order; filled by the loss kernel
+    int* dense_count = nullptr;        // (1)
+};
+// gverts (n,778,3) may be null; gtips (n,5,3) may be null (extra gradient on the 5 fingertip vertices).
+// With sp.gzero: flagged hands get dA and dX (all KP entries) from the fingertips alone; their gposed rows are not written.
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
-                    const float* gtips, float* gposed, float* dA, cudaStream_t st);
-int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st);
+                    const float* gtips, float* gposed, float* dA, cudaStream_t st, SparseGrad sp = SparseGrad(),
+                    float* dX = nullptr);
+// With sp.dense_list: only the listed rows of gposed are contracted (and only their dX rows written).
+int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp = SparseGrad());
 // orientation-only stages (fused layout only): cache L = R0^T (x - J0), then x = R0 L + J0 and its backward
 int launch_rigid_prep(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
 int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
 int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips, const float* gjoints, const float* Lv,
-                     const float* Lj, float* params_grad, cudaStream_t st);
+                     const float* Lj, float* params_grad, cudaStream_t st, SparseGrad sp = SparseGrad());
 // shape-only stages (fused layout only): cache (T_v | T_v c_v) per vertex, then the affine forward / backward in beta
 int launch_shape_prep(const ihmr_model* m, int n, HandSrc src, const float* off, const float* A, float* cache, cudaStream_t st);
 int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st);
 int launch_shape_bwd(const ihmr_model* m, int n, const float* cache, const float* gverts, const float* gtips, float* dA,
-                     float* dX, cudaStream_t st);
+                     float* dX, cudaStream_t st, SparseGrad sp = SparseGrad());
 // skinning forward with the blend T = W . A^T on tcgen05 (blend_tc.cu)
 int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st);
 // C[M,Nc] = A[M,K] . B[Nc,K]^T on tcgen05 with 3xTF32 splitting (blend_tc.cu)
+// rows / nrows (device, optional): row r of the product uses row rows[r] of A and of C, for r < *nrows <= M
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st);
+                       cudaStream_t st, const int* rows = nullptr, const int* nrows = nullptr);
 // C[M,N] = A[M,K] . B[K,N] on the FP32 pipe: reference for the tensor-core path (tests only)
 int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                            cudaStream_t st);
@@ -78,6 +89,7 @@ struct SdfArgs {
     float* per_vert = nullptr;         // (B,1556) or null
     float* origin = nullptr;           // (B,1556) or null
     float* gverts = nullptr;           // (B,2,778,3) or null
+    uint8_t* gzero = nullptr;          // (B,2) or null: 1 = this hand's gverts are identically zero and were NOT written
     float* gshift = nullptr;           // (B,3) or null
     float grad_scale = 1.0f;           // gverts/gshift = grad_scale * d losses[b]/d(.)
     float robustifier = 0.0f;

@@ -425,7 +425,8 @@ constexpr int SKB_SLICE = 288;          // vertices per slice (9 x 32)
 __global__ void __launch_bounds__(SKB_THREADS)
 k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
            const float* __restrict__ W4, const float* __restrict__ gverts, const float* __restrict__ gtips,
-           float* __restrict__ gposed, float* __restrict__ dA) {
+           float* __restrict__ gposed, float* __restrict__ dA, const uint8_t* __restrict__ gzero,
+           const float* __restrict__ DT, float* __restrict__ dX) {
     extern __shared__ float4 smem4[];
     float4* sW4 = smem4;                       // [4][778]
     float4* sG = sW4 + 4 * NV;                 // [778]  (g, 0)
@@ -465,6 +466,67 @@ k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, co
 
     for (int hh = 0; hh < nh; ++hh) {
         const size_t h = h0 + hh;
+        if (gzero && gzero[h]) {
+            // Vertex gradient identically zero (no penetration gradient on this hand): only the five fingertip
+            // vertices carry gradient.  dA and the whole dX row come from them directly; gposed is not written
+            // (the blend contraction skips this hand).
+            const int tips[5] = {744, 320, 443, 554, 671};
+            if (tid < 5) {
+                const int v = tips[tid];
+                float g[3] = {0.f, 0.f, 0.f}, vp[3];
+                if (gtips) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) g[c] = gtips[(h * 5 + tid) * 3 + c];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) vp[c] = vtemp[v * 3 + c] + off[h * LDN + v * 3 + c];
+                float T[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) T[i] = 0.f;
+#pragma unroll
+                for (int jt = 0; jt < 4; ++jt) {
+                    const float4 w4 = sW4[jt * NV + v];
+                    const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int ji = 0; ji < 4; ++ji) {
+                        const int j = jt * 4 + ji;
+                        const float4 r0 = sA[hh * 48 + j * 3 + 0], r1 = sA[hh * 48 + j * 3 + 1], r2 = sA[hh * 48 + j * 3 + 2];
+                        const float ww = wj[ji];
+                        T[0] += ww * r0.x; T[1] += ww * r0.y; T[2] += ww * r0.z;
+                        T[3] += ww * r1.x; T[4] += ww * r1.y; T[5] += ww * r1.z;
+                        T[6] += ww * r2.x; T[7] += ww * r2.y; T[8] += ww * r2.z;
+                    }
+                }
+                sG[tid] = make_float4(g[0], g[1], g[2], 0.f);
+                sP[tid] = make_float4(vp[0], vp[1], vp[2], 1.f);
+                // d v_posed of the tip, kept in sG[8 + tid]
+                sG[8 + tid] = make_float4(T[0] * g[0] + T[3] * g[1] + T[6] * g[2], T[1] * g[0] + T[4] * g[1] + T[7] * g[2],
+                                          T[2] * g[0] + T[5] * g[1] + T[8] * g[2], 0.f);
+            }
+            __syncthreads();
+            if (tid < 192) {                   // dA[j][r][c] = sum_tips W[v,j] g[r] [v_posed,1][c]
+                const int j = tid / 12, r = (tid % 12) >> 2, c = tid & 3;
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    const float w = reinterpret_cast<const float*>(&sW4[(j >> 2) * NV + tips[t]])[j & 3];
+                    acc += w * reinterpret_cast<const float*>(&sG[t])[r] * reinterpret_cast<const float*>(&sP[t])[c];
+                }
+                dA[h * 192 + tid] = acc;
+            }
+            if (dX && tid >= 192 && tid < 192 + KP) {      // dX[k] = sum_{tip,c} d v_posed[tip][c] D[k][3 tip_v + c]
+                const int k = tid - 192;
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < 5; ++t)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        acc += reinterpret_cast<const float*>(&sG[8 + t])[c] * DT[(size_t)(tips[t] * 3 + c) * KP + k];
+                dX[h * KP + k] = acc;
+            }
+            __syncthreads();
+            continue;
+        }
         // phase A (thread = vertex): d v_posed = T^T g, stash (g,0) and (v_posed,1)
         for (int v = tid; v < NV; v += SKB_THREADS) {
             float g[3] = {0.f, 0.f, 0.f}, vp[3];
@@ -598,18 +660,26 @@ k_rigid_xform(int n, HandSrc src, float* __restrict__ verts, float* __restrict__
 __global__ void __launch_bounds__(RG_THREADS)
 k_rigid_bwd(int n, HandSrc src, const float* __restrict__ gverts, const float* __restrict__ gtips,
             const float* __restrict__ gjoints, const float* __restrict__ Lv, const float* __restrict__ Lj,
-            float* __restrict__ params_grad) {
+            float* __restrict__ params_grad, const uint8_t* __restrict__ gzero) {
     __shared__ float red[9][RG_THREADS / 32];
     const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float M[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) M[i] = 0.f;
-    for (int i = tid; i < NV + NJ; i += RG_THREADS) {
+    // a hand without collision gradient: only the five fingertip vertices and the joints carry gradient
+    const bool sparse = gzero && gzero[h];
+    const int tips[5] = {744, 320, 443, 554, 671};
+    const int nitems = sparse ? 5 + NJ : NV + NJ;
+    for (int it = tid; it < nitems; it += RG_THREADS) {
+        const int i = sparse ? (it < 5 ? tips[it] : NV + it - 5) : it;
         float g[3];
         const float* l;
         if (i < NV) {
-            const float* gp = gverts + ((size_t)h * NV + i) * 3;
-            g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
+            g[0] = 0.f; g[1] = 0.f; g[2] = 0.f;
+            if (!sparse) {
+                const float* gp = gverts + ((size_t)h * NV + i) * 3;
+                g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
+            }
             const int tip = (i == 744) ? 0 : (i == 320) ? 1 : (i == 443) ? 2 : (i == 554) ? 3 : (i == 671) ? 4 : -1;
             if (tip >= 0) {
 #pragma unroll
@@ -667,9 +737,9 @@ int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv,
 }
 
 int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips, const float* gjoints, const float* Lv,
-                     const float* Lj, float* params_grad, cudaStream_t st) {
+                     const float* Lj, float* params_grad, cudaStream_t st, SparseGrad sp) {
     if (n <= 0) return IHMR_OK;
-    k_rigid_bwd<<<n, RG_THREADS, 0, st>>>(n, src, gverts, gtips, gjoints, Lv, Lj, params_grad);
+    k_rigid_bwd<<<n, RG_THREADS, 0, st>>>(n, src, gverts, gtips, gjoints, Lv, Lj, params_grad, sp.gzero);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
@@ -925,20 +995,30 @@ __device__ __forceinline__ void shape_issue_pair(const float4* cache, const floa
 __global__ void __launch_bounds__(SH_THREADS, 1)
 k_shape_bwd(int n, const float* __restrict__ W4, const float* __restrict__ Sv, const float4* __restrict__ cache,
             const float* __restrict__ gverts, const float* __restrict__ gtips, float* __restrict__ dA,
-            float* __restrict__ dX) {
+            float* __restrict__ dX, const uint8_t* __restrict__ gzero) {
     extern __shared__ float4 smem4[];
     float4* ring = smem4;                                                          // [SHB_STAGES][SHB_STAGE_F4]
     float* sPart = reinterpret_cast<float*>(ring + SHB_STAGES * SHB_STAGE_F4);      // [2][SH_WARPS][64]: 48 dta + 16 dbeta
     float* sTips = sPart + 2 * SH_WARPS * 64;                                       // [SHB_HPC][16]
     __shared__ __align__(8) unsigned long long bars[SHB_STAGES];
+    // Pairs (= frames) in which neither hand has a collision gradient (gzero) carry only fingertip gradients: they
+    // are not streamed at all (s_sparse) and are finished from five cache rows per hand at the end.
+    __shared__ int s_dense[SHB_HPC / 2], s_sparse[SHB_HPC / 2], s_nd, s_ns;
+    __shared__ float sQ[SHB_HPC][5][8];              // per sparse hand and fingertip: g (3), q = T^T g (3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h0 = blockIdx.x * SHB_HPC, nh = min(SHB_HPC, n - h0), npair = nh / 2;
     if (tid == 0) {
+        int nd = 0, ns = 0;
+        for (int p = 0; p < npair; ++p) {
+            if (gzero && gzero[h0 + 2 * p] && gzero[h0 + 2 * p + 1]) s_sparse[ns++] = p;
+            else s_dense[nd++] = p;
+        }
+        s_nd = nd; s_ns = ns;
         for (int k = 0; k < SHB_STAGES; ++k)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bars[k])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int k = 0; k < SHB_STAGES && k < npair; ++k)
-            shape_issue_pair(cache, gverts, (size_t)h0 + 2 * k, ring + k * SHB_STAGE_F4, &bars[k]);
+        for (int k = 0; k < SHB_STAGES && k < nd; ++k)
+            shape_issue_pair(cache, gverts, (size_t)h0 + 2 * s_dense[k], ring + k * SHB_STAGE_F4, &bars[k]);
     }
     for (int i = tid; i < nh * 15; i += SH_THREADS) sTips[(i / 15) * 16 + i % 15] = gtips ? gtips[(size_t)h0 * 15 + i] : 0.f;
     float sv[2][32];
@@ -951,20 +1031,23 @@ k_shape_bwd(int n, const float* __restrict__ W4, const float* __restrict__ Sv, c
         tip[sl] = (v == 744) ? 0 : (v == 320) ? 1 : (v == 443) ? 2 : (v == 554) ? 3 : (v == 671) ? 4 : -1;
     }
     const float4* W44 = reinterpret_cast<const float4*>(W4);
-    __syncthreads();                                            // barriers initialised, tips staged
-    for (int p = 0; p < npair; ++p) {
-        const int st = p % SHB_STAGES;
-        shape_wait(&bars[st], (p / SHB_STAGES) & 1);
+    __syncthreads();                                            // barriers initialised, tips staged, pair lists built
+    const int nd = s_nd, ns = s_ns;
+    for (int q = 0; q < nd; ++q) {
+        const int p = s_dense[q];
+        const int st = q % SHB_STAGES;
+        shape_wait(&bars[st], (q / SHB_STAGES) & 1);
         const float4* stage = ring + st * SHB_STAGE_F4;
         const float* G = reinterpret_cast<const float*>(stage + 2 * 3 * NV);
 #pragma unroll
         for (int hl = 0; hl < 2; ++hl) {
             const int hh = 2 * p + hl;
             const float4* rows = stage + hl * 3 * NV;
+            const bool hzero = gzero && gzero[h0 + hh];         // its vertex gradients were not written: zeros
             float g[2][3];
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
-                const bool ok = tid + sl * SH_THREADS < NV;
+                const bool ok = tid + sl * SH_THREADS < NV && !hzero;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) g[sl][c] = ok ? G[(hl * NV + vv[sl]) * 3 + c] : 0.f;
                 if (tip[sl] >= 0) {
@@ -1012,8 +1095,8 @@ k_shape_bwd(int n, const float* __restrict__ W4, const float* __restrict__ Sv, c
             }
         }
         __syncthreads();                                        // partial sums visible, the stage is free
-        if (tid == 0 && p + SHB_STAGES < npair)
-            shape_issue_pair(cache, gverts, (size_t)h0 + 2 * (p + SHB_STAGES), ring + st * SHB_STAGE_F4, &bars[st]);
+        if (tid == 0 && q + SHB_STAGES < nd)
+            shape_issue_pair(cache, gverts, (size_t)h0 + 2 * s_dense[q + SHB_STAGES], ring + st * SHB_STAGE_F4, &bars[st]);
         for (int i = tid; i < 2 * (192 + KP); i += SH_THREADS) {
             const int hl = i / (192 + KP), x = i % (192 + KP);
             const size_t h = (size_t)h0 + 2 * p + hl;
@@ -1036,6 +1119,47 @@ k_shape_bwd(int n, const float* __restrict__ W4, const float* __restrict__ Sv, c
             }
         }
         __syncthreads();                                        // sPart is rewritten by the next pair
+    }
+    // ---- pairs without collision gradient: the same two sums over the five fingertip vertices only
+    if (ns > 0) {
+        const int tips[5] = {744, 320, 443, 554, 671};
+        for (int i = tid; i < ns * 2 * 5; i += SH_THREADS) {
+            const int hh = 2 * s_sparse[i / 10] + (i % 10) / 5, t = i % 5, v = tips[t];
+            const float4* rows = cache + ((size_t)h0 + hh) * 3 * NV;
+            const float4 r0 = rows[v], r1 = rows[NV + v], r2 = rows[2 * NV + v];
+            const float g[3] = {sTips[hh * 16 + t * 3], sTips[hh * 16 + t * 3 + 1], sTips[hh * 16 + t * 3 + 2]};
+            float* o = sQ[hh][t];
+            o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
+            o[3] = r0.x * g[0] + r1.x * g[1] + r2.x * g[2];
+            o[4] = r0.y * g[0] + r1.y * g[1] + r2.y * g[2];
+            o[5] = r0.z * g[0] + r1.z * g[1] + r2.z * g[2];
+        }
+        __syncthreads();
+        for (int i = tid; i < ns * 2 * (192 + KP); i += SH_THREADS) {
+            const int hh = 2 * s_sparse[i / (2 * (192 + KP))] + (i / (192 + KP)) % 2, x = i % (192 + KP);
+            const size_t h = (size_t)h0 + hh;
+            float sum = 0.f;
+            if (x < 192) {
+                if ((x & 3) == 3) {
+                    const int j = x / 12, r = (x % 12) / 4;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) sum += W4[((size_t)(j >> 2) * NV + tips[t]) * 4 + (j & 3)] * sQ[hh][t][r];
+                }
+                dA[h * 192 + x] = sum;
+            } else {
+                const int k = x - 192;
+                if (k >= NPF && k < NPF + NB) {
+#pragma unroll
+                    for (int t = 0; t < 5; ++t)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int e = c * NB + (k - NPF);          // entry e of the vertex's shape row: plane e / 4, lane e % 4
+                            sum += Sv[((size_t)(e >> 2) * NV + tips[t]) * 4 + (e & 3)] * sQ[hh][t][3 + c];
+                        }
+                }
+                dX[h * KP + k] = sum;
+            }
+        }
     }
 }
 
@@ -1065,13 +1189,13 @@ int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, co
 }
 
 int launch_shape_bwd(const ihmr_model* m, int n, const float* cache, const float* gverts, const float* gtips, float* dA,
-                     float* dX, cudaStream_t st) {
+                     float* dX, cudaStream_t st, SparseGrad sp) {
     if (n <= 0) return IHMR_OK;
     if (n & 1) { set_error("shape_bwd: the hands come in pairs (two per frame)"); return IHMR_E_INVALID; }
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_shape_bwd, SHAPE_BWD_SMEM, configured)) return rc;
     k_shape_bwd<<<(n + SHB_HPC - 1) / SHB_HPC, SH_THREADS, SHAPE_BWD_SMEM, st>>>(n, m->W4, m->Sv, reinterpret_cast<const float4*>(cache),
-                                                                               gverts, gtips, dA, dX);
+                                                                               gverts, gtips, dA, dX, sp.gzero);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
@@ -1122,9 +1246,9 @@ int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cud
     return launch_gemm_tf32x3(n, LDN, KP, X, KP, m->DT, KP, off, LDN, st);
 }
 
-int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st) {
-    // dX (n x 160) = gposed (n x 2336) . D^T  with D (160 x 2336) K-major
-    return launch_gemm_tf32x3(n, KP, LDN, gposed, LDN, m->D, LDN, dX, KP, st);
+int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp) {
+    // dX (n x 160) = gposed (n x 2336) . D^T  with D (160 x 2336) K-major; with a dense-hand list only those rows
+    return launch_gemm_tf32x3(n, KP, LDN, gposed, LDN, m->D, LDN, dX, KP, st, sp.dense_list, sp.dense_count);
 }
 
 int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
@@ -1142,12 +1266,13 @@ int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A
 }
 
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,
-                    const float* gtips, float* gposed, float* dA, cudaStream_t st) {
+                    const float* gtips, float* gposed, float* dA, cudaStream_t st, SparseGrad sp, float* dX) {
     if (n <= 0) return IHMR_OK;
+    if (sp.gzero && !dX) { set_error("skin_bwd: the sparse path needs dX"); return IHMR_E_INVALID; }
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_skin_bwd, SKIN_BWD_SMEM, configured)) return rc;
     k_skin_bwd<<<(n + SK_HPC - 1) / SK_HPC, SKB_THREADS, SKIN_BWD_SMEM, st>>>(n, off, A, m->vtemp, m->W4,
-                                                                           gverts, gtips, gposed, dA);
+                                                                           gverts, gtips, gposed, dA, sp.gzero, m->DT, dX);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }

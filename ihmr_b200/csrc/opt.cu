@@ -20,6 +20,9 @@ struct FrameLossArgs {
     const float* col_loss;        // (B) unweighted, masked collision loss from the sdf kernels, or
     const float* col_parts;       // (B,2) its two unmasked direction sums (loss = mask * (p0 + p1) / 4)
     const float* gshift_col;      // (B,3) collision gradient w.r.t. the left-hand shift (scaled) or null
+    const uint8_t* gzero;         // (B,2) or null: hands without vertex gradient ...
+    int* dense_list;              // ... the others are appended here (any order) for the blend contraction
+    int* dense_count;
     // outputs
     float* gjoints16;             // (B,2,16,3) or null
     float* gtips;                 // (B,2,5,3) or null
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_frame_loss(FrameLossArgs a) {
         if (r1 >= 0 && t == r1) { ga[0] -= s0; ga[1] -= s1; ga[2] -= s2; }
     }
     gJ[0] += ga[0]; gJ[1] += ga[1]; gJ[2] += ga[2];
+    if (a.dense_list && t < 2 && !a.gzero[b * 2 + t]) a.dense_list[atomicAdd(a.dense_count, 1)] = b * 2 + t;
     // ---- shift gradient: all left-hand joints move with it
     float gs[3];
 #pragma unroll
@@ -408,6 +412,8 @@ struct OptWs {
     int* take;
     void* sdf_ws;             // scratch of the penetration kernels (sdf_ws_bytes)
     uint16_t* sdf_hints;      // nearest-face seeds the penetration kernel carries from one iteration to the next
+    uint8_t* gzero;           // (N) hands whose collision gradient is identically zero this iteration
+    int* dense_list;          // (N) the other hands, [N] = their count
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -445,6 +451,8 @@ static size_t opt_ws_layout(void* base, int B, OptWs* out) {
     w.shape_cache = (float*)take((size_t)n * NV * 12 * 4);
     w.sdf_ws = take(sdf_ws_bytes(B));
     w.sdf_hints = (uint16_t*)take(sdf_hint_bytes(B));
+    w.gzero = (uint8_t*)take((size_t)n);
+    w.dense_list = (int*)take((size_t)(n + 1) * 4);
     if (out) *out = w;
     return used;
 }
@@ -503,6 +511,7 @@ struct IterPlan {
                               // carry no gradient, their loss part is needed at snapshots only
     int rigid = 0;            // orientation-only stage: 1 = first iteration (generic forward, then cache the
                               // root-local geometry), 2 = later iterations (x = R0 L + J0); backward is rigid in both
+    bool dense_grad = false;  // (with IHMR_STAGE_GENERIC_KERNELS) no fingertip-only short path for hands without collision gradient
     int shape = 0;            // shape-only stage: 1 = first iteration (generic forward, then cache T_v | T_v c_v),
                               // 2 = later iterations (affine in beta); backward is the affine one in both
 };
@@ -516,7 +525,8 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot, bool ge
     p.mano_bwd = live_mano;
     p.blend_bwd = live_blend;
     p.sdf_skip_grid = (!live_mano && !snapshot) ? 2 : 0;
-    if (generic) return p;      // IHMR_STAGE_GENERIC_KERNELS: every stage on the generic kernel chain
+    p.dense_grad = generic;
+    if (generic) return p;      // IHMR_STAGE_GENERIC_KERNELS: every stage on the generic kernel chain, every hand dense
     if ((mask & (IHMR_P_R_SHAPE | IHMR_P_L_SHAPE)) &&
         !(mask & (IHMR_P_R_POSE | IHMR_P_L_POSE | IHMR_P_R_ORIENT | IHMR_P_L_ORIENT))) {   // opt_default stage 3
         p.shape = first ? 1 : 2;
@@ -554,23 +564,35 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
     sa.ws = w.sdf_ws; sa.hints = carry_hints ? w.sdf_hints : nullptr; sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
+    // generic backward chain: hands without collision gradient take the fingertip-only path (flags from the sdf kernels,
+    // list of the others from the loss kernel)
+    SparseGrad sp;
+    if (sa.gverts && !plan.dense_grad) {
+        sp.gzero = w.gzero;
+        sa.gzero = w.gzero;
+        if (plan.blend_bwd) {               // the blend contraction's backward runs on the list of the other hands
+            sp.dense_list = w.dense_list; sp.dense_count = w.dense_list + 2 * B;
+            IHMR_CUDA_OK(cudaMemsetAsync(sp.dense_count, 0, 4, st));
+        }
+    }
     sa.grad_scale = stg->w_collision / (float)bs_norm;
     sa.skip_grid_mask = plan.sdf_skip_grid;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
     IHMR_TICK(prof, 4);
     la.gshift_col = w.gshift;
+    la.gzero = sp.gzero; la.dense_list = sp.dense_list; la.dense_count = sp.dense_count;
     la.col_loss = nullptr; la.col_parts = sdf_ws_parts(w.sdf_ws, B);
     la.gjoints16 = w.gjoints; la.gtips = w.gtips; la.grad = w.grad;
     la.j2d_batch = w.j2d_b; la.j3d_batch = w.j3d_b;
     k_frame_loss<<<B, FL_THREADS, 0, st>>>(la);
     IHMR_LAUNCH_OK();
     IHMR_TICK(prof, 5);
-    if (plan.mano_bwd && !plan.shape && (rc = launch_skin_bwd(m, 2 * B, w.mano.off, w.mano.A, w.gverts, w.gtips, w.mano.gposed, w.mano.dA, st))) return rc;
-    if (plan.shape && (rc = launch_shape_bwd(m, 2 * B, w.shape_cache, w.gverts, w.gtips, w.mano.dA, w.mano.dX, st))) return rc;
+    if (plan.mano_bwd && !plan.shape && (rc = launch_skin_bwd(m, 2 * B, w.mano.off, w.mano.A, w.gverts, w.gtips, w.mano.gposed, w.mano.dA, st, sp, w.mano.dX))) return rc;
+    if (plan.shape && (rc = launch_shape_bwd(m, 2 * B, w.shape_cache, w.gverts, w.gtips, w.mano.dA, w.mano.dX, st, sp))) return rc;
     IHMR_TICK(prof, 6);
-    if (plan.blend_bwd && (rc = launch_blend_bwd(m, 2 * B, w.mano.gposed, w.mano.dX, st))) return rc;
+    if (plan.blend_bwd && (rc = launch_blend_bwd(m, 2 * B, w.mano.gposed, w.mano.dX, st, sp))) return rc;
     IHMR_TICK(prof, 7);
-    if (plan.rigid && (rc = launch_rigid_bwd(2 * B, src, w.gverts, w.gtips, w.gjoints, w.mano.gposed, w.mano.dA, w.grad, st))) return rc;
+    if (plan.rigid && (rc = launch_rigid_bwd(2 * B, src, w.gverts, w.gtips, w.gjoints, w.mano.gposed, w.mano.dA, w.grad, st, sp))) return rc;
     HandGrad hg;
     hg.params_grad = w.grad;
     if (plan.mano_bwd && (rc = launch_pose_bwd(m, 2 * B, src, w.mano.dA, w.gjoints, (plan.blend_bwd || plan.shape) ? w.mano.dX : nullptr, hg, st))) return rc;

@@ -52,7 +52,7 @@ constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
 #define SDF_PHI_CAP 1024            // voxels evaluated per pass
 #endif
 #ifndef SDF_Q_CAP
-#define SDF_Q_CAP 2560              // queued (voxel, face) candidates / (face, column) ray items
+#define SDF_Q_CAP 2304              // queued (voxel, face) candidates / (face, column) ray items
 #endif
 #ifndef SDF_V_CHUNK
 #define SDF_V_CHUNK 128             // voxels per search round
@@ -103,7 +103,7 @@ struct __align__(16) SdfSmem {
     uint16_t coloff[G * G];     // exclusive prefix of popc(work)
     uint32_t worklist[PHI_CAP]; // voxels of the current pass as packed Q8 centres: 8x+4 | (8y+4) << 8 | (8z+4) << 16
     uint32_t best[PHI_CAP];     // bit pattern of the best squared distance (>= 0: orders like uint); then phi
-    uint16_t hintw[PHI_CAP];    // face slot behind best (to rounding): next iteration's seed
+    uint32_t hintw[PHI_CAP];    // face slot behind best (to rounding): next iteration's seed
     uint32_t queue[Q_CAP];      // (voxel index << 16) | face slot;  parity: (face slot << 10) | column
     uint2 cl_box[NCL];          // union of the cluster's face boxes, same packing as fbox
     uint2 fbox[NCL * 32];       // per face (cluster-table order): box quantised outwards to Q8;
@@ -262,10 +262,10 @@ __device__ __forceinline__ float voxel_face_dist2(const SdfSmem& s, const ushort
 }
 
 // one exact (voxel, face) test; the result lowers the voxel's best squared distance.  hintw follows the
-// improvements without an ordering guarantee between concurrent improvers: it is a seed, not a result.
+// improvements (atomic exchange, no ordering between concurrent improvers): it is a seed, not a result.
 __device__ __forceinline__ void pair_test(SdfSmem& s, const ushort4* __restrict__ cl_tri, int vi, int slot) {
     const uint32_t bits = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[vi], slot));
-    if (bits < atomicMin(&s.best[vi], bits)) s.hintw[vi] = (uint16_t)slot;
+    if (bits < atomicMin(&s.best[vi], bits)) atomicExch(&s.hintw[vi], (uint32_t)slot);
 }
 
 // packed Q8 voxel centre -> index into the hint table: the low bits of (x, y, z), so that a block of
@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) k_sdf_prep(int B, SdfArgs a, 
             const size_t ov = (size_t)b * (2 * NV) + o * NV;
             if (a.per_vert) for (int v = lane; v < NV; v += 32) a.per_vert[ov + v] = 0.f;
             if (a.origin) for (int v = lane; v < NV; v += 32) a.origin[ov + v] = 0.f;
-            if (a.gverts) { float* g = a.gverts + ov * 3; for (int i = lane; i < NV * 3; i += 32) g[i] = 0.f; }
+            if (a.gzero) { if (lane == 0) a.gzero[b * 2 + o] = 1; }      // consumers skip this hand's vertex gradients
+            else if (a.gverts) { float* g = a.gverts + ov * 3; for (int i = lane; i < NV * 3; i += 32) g[i] = 0.f; }
             if (a.gshift && o == 1 && lane < 3) a.gshift[(size_t)b * 3 + lane] = 0.f;
             if (a.stats && lane == 0) a.stats[b * 32 + 16 + h] = 1;
         };
@@ -741,7 +742,7 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                     }
                     if (lane < nt) {
                         s.best[t0 + lane] = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[t0 + lane], myseed));
-                        s.hintw[t0 + lane] = (uint16_t)myseed;
+                        s.hintw[t0 + lane] = (uint32_t)myseed;
                     }
                     __syncwarp();
                     for (int k = 0; k < nt; ++k) {
@@ -804,7 +805,8 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
                 if (a.per_vert) a.per_vert[ov0 + v] = rho0;
                 if (a.origin) a.origin[ov0 + v] = 0.f;
             }
-            if (a.gverts) { float* gp = a.gverts + ov0 * 3; for (int i = tid; i < NV * 3; i += SDF_THREADS) gp[i] = 0.f; }
+            if (a.gzero) { if (tid == 0) a.gzero[b * 2 + o] = 1; }
+            else if (a.gverts) { float* gp = a.gverts + ov0 * 3; for (int i = tid; i < NV * 3; i += SDF_THREADS) gp[i] = 0.f; }
             if (tid == 0) w.parts[b * 2 + h] = 0.f;
             if (want_shift && tid < 3) a.gshift[(size_t)b * 3 + tid] = 0.f;
             SDF_STAT(9)
@@ -866,6 +868,7 @@ k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* _
         }
         block_sum4(sums, want_shift ? 4 : 1, s.red);
         if (tid == 0) w.parts[b * 2 + h] = sums[0];
+        if (a.gzero && tid == 0) a.gzero[b * 2 + o] = 0;
         if (want_shift && tid >= 1 && tid < 4) a.gshift[(size_t)b * 3 + (tid - 1)] = sums[tid];
         SDF_STAT(9)
     }

@@ -129,7 +129,9 @@ enum { IHMR_P_CAM = 1, IHMR_P_TRANS = 2, IHMR_P_R_ORIENT = 4, IHMR_P_R_POSE = 8,
 enum { IHMR_LOSS_JOINTS_3D_P = 0, IHMR_LOSS_COLLISION = 1, IHMR_LOSS_JOINTS_2D_P = 2 };
 enum { IHMR_OPT_ADAM = 0, IHMR_OPT_SGD = 1 };
 /* IHMR_STAGE_GENERIC_KERNELS: run this stage on the generic kernel chain even where a specialised rewrite
- * exists (orientation-only and shape-only stages); the tests compare the two. */
+ * exists (orientation-only and shape-only stages), and push every hand through the dense backward kernels even
+ * when its collision gradient is identically zero (normally such hands take a fingertip-only path); the tests
+ * compare the two. */
 enum { IHMR_STAGE_GENERIC_KERNELS = 1 };
 
 typedef struct {
