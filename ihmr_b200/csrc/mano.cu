@@ -425,8 +425,8 @@ constexpr int SKB_SLICE = 288;          // vertices per slice (9 x 32)
 __global__ void __launch_bounds__(SKB_THREADS)
 k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
            const float* __restrict__ W4, const float* __restrict__ gverts, const float* __restrict__ gtips,
-           float* __restrict__ gposed, float* __restrict__ dA, const uint8_t* __restrict__ gzero,
-           const float* __restrict__ DT, float* __restrict__ dX) {
+           float* __restrict__ gposed, float* __restrict__ dA, const int* __restrict__ dense_list,
+           const int* __restrict__ dense_count) {
     extern __shared__ float4 smem4[];
     float4* sW4 = smem4;                       // [4][778]
     float4* sG = sW4 + 4 * NV;                 // [778]  (g, 0)
@@ -434,11 +434,14 @@ k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, co
     float4* sA = sP + NV;                      // [SK_HPC][48]
     float* sPart = reinterpret_cast<float*>(sA + SK_HPC * 48);   // [SKB_KSLICES][192]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // With a list (hands that do have a vertex gradient) the CTA takes 8 list entries; CTAs beyond the list leave.
     const int h0 = blockIdx.x * SK_HPC;
-    const int nh = min(SK_HPC, n - h0);
+    const int ntot = dense_list ? min(n, *dense_count) : n;
+    if (h0 >= ntot) return;
+    const int nh = min(SK_HPC, ntot - h0);
 
     // Stage the skinning weights (49.8 KB, tile-major) and this CTA's joint transforms with the TMA engine:
-    // two 1-D bulk copies global -> shared that complete on an mbarrier, issued by one thread while the
+    // 1-D bulk copies global -> shared that complete on an mbarrier, issued by one thread while the
     // others go straight to waiting (no register round trip, no per-thread address arithmetic).
     __shared__ __align__(8) uint64_t tma_bar;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
@@ -450,8 +453,14 @@ k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, co
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(W4_BYTES + a_bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      :: "r"((uint32_t)__cvta_generic_to_shared(sW4)), "l"(W4), "r"(W4_BYTES), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"((uint32_t)__cvta_generic_to_shared(sA)), "l"(A + (size_t)h0 * 192), "r"(a_bytes), "r"(bar) : "memory");
+        if (!dense_list) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(sA)), "l"(A + (size_t)h0 * 192), "r"(a_bytes), "r"(bar) : "memory");
+        } else {
+            for (int hh = 0; hh < nh; ++hh)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"((uint32_t)__cvta_generic_to_shared(sA + hh * 48)), "l"(A + (size_t)dense_list[h0 + hh] * 192), "r"(768u), "r"(bar) : "memory");
+        }
     }
     __syncthreads();                                   // the barrier word is initialised before anyone polls it
     {
@@ -465,68 +474,7 @@ k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, co
     }
 
     for (int hh = 0; hh < nh; ++hh) {
-        const size_t h = h0 + hh;
-        if (gzero && gzero[h]) {
-            // Vertex gradient identically zero (no penetration gradient on this hand): only the five fingertip
-            // vertices carry gradient.  dA and the whole dX row come from them directly; gposed is not written
-            // (the blend contraction skips this hand).
-            const int tips[5] = {744, 320, 443, 554, 671};
-            if (tid < 5) {
-                const int v = tips[tid];
-                float g[3] = {0.f, 0.f, 0.f}, vp[3];
-                if (gtips) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) g[c] = gtips[(h * 5 + tid) * 3 + c];
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) vp[c] = vtemp[v * 3 + c] + off[h * LDN + v * 3 + c];
-                float T[9];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) T[i] = 0.f;
-#pragma unroll
-                for (int jt = 0; jt < 4; ++jt) {
-                    const float4 w4 = sW4[jt * NV + v];
-                    const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                    for (int ji = 0; ji < 4; ++ji) {
-                        const int j = jt * 4 + ji;
-                        const float4 r0 = sA[hh * 48 + j * 3 + 0], r1 = sA[hh * 48 + j * 3 + 1], r2 = sA[hh * 48 + j * 3 + 2];
-                        const float ww = wj[ji];
-                        T[0] += ww * r0.x; T[1] += ww * r0.y; T[2] += ww * r0.z;
-                        T[3] += ww * r1.x; T[4] += ww * r1.y; T[5] += ww * r1.z;
-                        T[6] += ww * r2.x; T[7] += ww * r2.y; T[8] += ww * r2.z;
-                    }
-                }
-                sG[tid] = make_float4(g[0], g[1], g[2], 0.f);
-                sP[tid] = make_float4(vp[0], vp[1], vp[2], 1.f);
-                // d v_posed of the tip, kept in sG[8 + tid]
-                sG[8 + tid] = make_float4(T[0] * g[0] + T[3] * g[1] + T[6] * g[2], T[1] * g[0] + T[4] * g[1] + T[7] * g[2],
-                                          T[2] * g[0] + T[5] * g[1] + T[8] * g[2], 0.f);
-            }
-            __syncthreads();
-            if (tid < 192) {                   // dA[j][r][c] = sum_tips W[v,j] g[r] [v_posed,1][c]
-                const int j = tid / 12, r = (tid % 12) >> 2, c = tid & 3;
-                float acc = 0.f;
-#pragma unroll
-                for (int t = 0; t < 5; ++t) {
-                    const float w = reinterpret_cast<const float*>(&sW4[(j >> 2) * NV + tips[t]])[j & 3];
-                    acc += w * reinterpret_cast<const float*>(&sG[t])[r] * reinterpret_cast<const float*>(&sP[t])[c];
-                }
-                dA[h * 192 + tid] = acc;
-            }
-            if (dX && tid >= 192 && tid < 192 + KP) {      // dX[k] = sum_{tip,c} d v_posed[tip][c] D[k][3 tip_v + c]
-                const int k = tid - 192;
-                float acc = 0.f;
-#pragma unroll
-                for (int t = 0; t < 5; ++t)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        acc += reinterpret_cast<const float*>(&sG[8 + t])[c] * DT[(size_t)(tips[t] * 3 + c) * KP + k];
-                dX[h * KP + k] = acc;
-            }
-            __syncthreads();
-            continue;
-        }
+        const size_t h = dense_list ? (size_t)dense_list[h0 + hh] : (size_t)(h0 + hh);
         // phase A (thread = vertex): d v_posed = T^T g, stash (g,0) and (v_posed,1)
         for (int v = tid; v < NV; v += SKB_THREADS) {
             float g[3] = {0.f, 0.f, 0.f}, vp[3];
@@ -606,6 +554,61 @@ k_skin_bwd(int n, const float* __restrict__ off, const float* __restrict__ A, co
         // the next hand's phase A only touches sG/sP (all phase-B readers are past the barrier
         // above); its phase-B writes to sPart come after its own first barrier, i.e. after the
         // reads just above in program order of those threads and a barrier for the others.
+    }
+}
+
+// Hands whose vertex gradient is identically zero (no penetration gradient: flagged by the sdf kernels): only the
+// five fingertip vertices carry gradient.  One warp per hand: dA and the whole dX row come from them directly;
+// gposed is not written (the blend contraction skips these hands).
+__global__ void __launch_bounds__(256)
+k_skin_bwd_tips(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
+                const float* __restrict__ Wt, const float* __restrict__ gtips, const uint8_t* __restrict__ gzero,
+                const float* __restrict__ DT, float* __restrict__ dA, float* __restrict__ dX) {
+    __shared__ float sT[8][5][12];          // per warp and fingertip: g (3), [v_posed, 1] (4), d v_posed (3)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t h = (size_t)blockIdx.x * 8 + warp;
+    if (h >= (size_t)n || !gzero[h]) return;
+    const int tips[5] = {744, 320, 443, 554, 671};
+    if (lane < 5) {
+        const int v = tips[lane];
+        float g[3] = {0.f, 0.f, 0.f}, vp[3], T[9];
+        if (gtips) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c] = gtips[(h * 5 + lane) * 3 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vp[c] = vtemp[v * 3 + c] + off[h * LDN + v * 3 + c];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) T[i] = 0.f;
+        for (int j = 0; j < NJ; ++j) {
+            const float ww = Wt[j * NV + v];
+            const float* a = A + h * 192 + j * 12;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[r * 3 + c] += ww * a[r * 4 + c];
+        }
+        float* o = sT[warp][lane];
+        o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
+        o[3] = vp[0]; o[4] = vp[1]; o[5] = vp[2]; o[6] = 1.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[7 + c] = T[0 * 3 + c] * g[0] + T[1 * 3 + c] * g[1] + T[2 * 3 + c] * g[2];
+    }
+    __syncwarp();
+    for (int x = lane; x < 192; x += 32) {       // dA[j][r][c] = sum_tips W[v,j] g[r] [v_posed,1][c]
+        const int j = x / 12, r = (x % 12) >> 2, c = x & 3;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) acc += Wt[j * NV + tips[t]] * sT[warp][t][r] * sT[warp][t][3 + c];
+        dA[h * 192 + x] = acc;
+    }
+    for (int k = lane; k < KP; k += 32) {         // dX[k] = sum_{tip,c} d v_posed[tip][c] D[k][3 tip_v + c]
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc += sT[warp][t][7 + c] * DT[(size_t)(tips[t] * 3 + c) * KP + k];
+        dX[h * KP + k] = acc;
     }
 }
 
@@ -1271,9 +1274,14 @@ int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A
     if (sp.gzero && !dX) { set_error("skin_bwd: the sparse path needs dX"); return IHMR_E_INVALID; }
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_skin_bwd, SKIN_BWD_SMEM, configured)) return rc;
+    if (sp.gzero && !sp.dense_list) { set_error("skin_bwd: the sparse path needs the list of dense hands"); return IHMR_E_INVALID; }
     k_skin_bwd<<<(n + SK_HPC - 1) / SK_HPC, SKB_THREADS, SKIN_BWD_SMEM, st>>>(n, off, A, m->vtemp, m->W4,
-                                                                           gverts, gtips, gposed, dA, sp.gzero, m->DT, dX);
+                                                                           gverts, gtips, gposed, dA, sp.dense_list, sp.dense_count);
     IHMR_LAUNCH_OK();
+    if (sp.gzero) {
+        k_skin_bwd_tips<<<(n + 7) / 8, 256, 0, st>>>(n, off, A, m->vtemp, m->Wt, gtips, sp.gzero, m->DT, dA, dX);
+        IHMR_LAUNCH_OK();
+    }
     return IHMR_OK;
 }
 

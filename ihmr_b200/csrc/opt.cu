@@ -570,10 +570,9 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     if (sa.gverts && !plan.dense_grad) {
         sp.gzero = w.gzero;
         sa.gzero = w.gzero;
-        if (plan.blend_bwd) {               // the blend contraction's backward runs on the list of the other hands
-            sp.dense_list = w.dense_list; sp.dense_count = w.dense_list + 2 * B;
-            IHMR_CUDA_OK(cudaMemsetAsync(sp.dense_count, 0, 4, st));
-        }
+        // the dense skinning backward and the blend contraction's backward run on the list of the other hands
+        sp.dense_list = w.dense_list; sp.dense_count = w.dense_list + 2 * B;
+        IHMR_CUDA_OK(cudaMemsetAsync(sp.dense_count, 0, 4, st));
     }
     sa.grad_scale = stg->w_collision / (float)bs_norm;
     sa.skip_grid_mask = plan.sdf_skip_grid;

@@ -70,10 +70,12 @@ constexpr int SDF_HDR = 40;         // floats per frame header (see k_sdf_prep)
 constexpr float Q8_TO_D2 = 1.0f / 16384.0f;         // Q8 units squared -> normalised units squared
 constexpr float Q4D2_TO_D2 = 0.25f * Q8_TO_D2;      // qbox_4d2 units -> normalised units squared
 
+constexpr int SDF_BUCKETS = 4;      // work items are drawn heaviest bucket first (longest-processing-time-first: short tail)
+
 struct SdfWs {
-    uint32_t* counters;   // [0] items appended by k_sdf_prep, [1] ticket of k_sdf_dir
+    uint32_t* counters;   // [0..3] items appended by k_sdf_prep per cost bucket, [4] ticket of k_sdf_dir
     float* hdr;           // (B, SDF_HDR)
-    uint32_t* items;      // (2B) frame * 2 + grid hand
+    uint32_t* items;      // (SDF_BUCKETS, 2B) frame * 2 + grid hand
     float* parts;         // (B, 2) sum of rho over the query vertices of each direction
     float* spill;         // (SDF_MAX_GRID, SDF_SPILL)
 };
@@ -81,7 +83,7 @@ struct SdfWs {
 static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t sdf_ws_bytes(int B) {
-    return 256 + up256((size_t)B * SDF_HDR * 4) + up256((size_t)B * 2 * 4) + up256((size_t)B * 2 * 4) +
+    return 256 + up256((size_t)B * SDF_HDR * 4) + up256((size_t)SDF_BUCKETS * B * 2 * 4) + up256((size_t)B * 2 * 4) +
            up256((size_t)SDF_MAX_GRID * SDF_SPILL * 4);
 }
 
@@ -90,7 +92,7 @@ static SdfWs sdf_ws_carve(void* base, int B) {
     SdfWs w;
     w.counters = reinterpret_cast<uint32_t*>(p); p += 256;
     w.hdr = reinterpret_cast<float*>(p); p += up256((size_t)B * SDF_HDR * 4);
-    w.items = reinterpret_cast<uint32_t*>(p); p += up256((size_t)B * 2 * 4);
+    w.items = reinterpret_cast<uint32_t*>(p); p += up256((size_t)SDF_BUCKETS * B * 2 * 4);
     w.parts = reinterpret_cast<float*>(p); p += up256((size_t)B * 2 * 4);
     w.spill = reinterpret_cast<float*>(p);
     return w;
@@ -290,11 +292,11 @@ __device__ __forceinline__ int lat_hi(uint32_t hi) { return ((int)hi - 4) >> 3; 
 constexpr int PREP_WARPS = 8;
 
 __global__ void __launch_bounds__(PREP_WARPS * 32) k_sdf_prep(int B, SdfArgs a, SdfWs w) {
-    __shared__ uint32_t s_cnt, s_base;
-    __shared__ uint32_t s_items[2 * PREP_WARPS];
+    __shared__ uint32_t s_cnt[SDF_BUCKETS], s_base[SDF_BUCKETS];
+    __shared__ uint32_t s_items[SDF_BUCKETS][2 * PREP_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * PREP_WARPS + warp;
-    if (threadIdx.x == 0) s_cnt = 0u;
+    if (threadIdx.x < SDF_BUCKETS) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
     if (b < B) {
         const bool xform = (a.joints != nullptr);
@@ -375,7 +377,15 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) k_sdf_prep(int B, SdfArgs a, 
             const bool may = olo[0] <= dh[13] && ohi[1] >= dh[11] && olo[1] <= dh[14] && ohi[2] >= dh[12] && olo[2] <= dh[15];
             const bool skipped = (a.skip_grid_mask >> h) & 1;      // this direction is not wanted at all
             if (may && !skipped) {
-                if (lane == 0) s_items[atomicAdd(&s_cnt, 1u)] = (uint32_t)(b * 2 + h);
+                // cost proxy: volume (in voxels of grid hand h) of the query hand's box inside the grid hand's reject box
+                float vol = 1.0f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) vol *= fmaxf(0.f, fminf(ohi[c], dh[13 + c]) - fmaxf(olo[c], dh[10 + c]));
+                const float vs = dh[3] * (2.0f / G);
+                vol /= vs * vs * vs;
+                const int bucket = vol >= 1500.f ? 0 : vol >= 500.f ? 1 : vol >= 100.f ? 2 : 3;
+                if (lane == 0) s_items[bucket][atomicAdd(&s_cnt[bucket], 1u)] = (uint32_t)(b * 2 + h);
+                if (a.stats && lane == 0) a.stats[b * 32 + 14 + h] = (int)fminf(vol, 1e9f);
                 return;
             }
             if (lane == 0) w.parts[b * 2 + h] = 0.f;
@@ -393,9 +403,10 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) k_sdf_prep(int B, SdfArgs a, 
         direction(1, dp[1], lo[0], hi[0]);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(&w.counters[0], s_cnt);
+    if (threadIdx.x < SDF_BUCKETS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&w.counters[threadIdx.x], s_cnt[threadIdx.x]);
     __syncthreads();
-    if (threadIdx.x < s_cnt) w.items[s_base + threadIdx.x] = s_items[threadIdx.x];
+    for (int k = 0; k < SDF_BUCKETS; ++k)
+        if (threadIdx.x < s_cnt[k]) w.items[(size_t)k * 2 * B + s_base[k] + threadIdx.x] = s_items[k][threadIdx.x];
 }
 
 // losses[b] = mask * (part_0 + part_1) / 4                                              (A6)
@@ -420,20 +431,33 @@ __global__ void k_sdf_finish(int B, const float* __restrict__ parts, const float
 // parity, scan, worklist, seeds + candidates, exact tests, finish, sample + outputs)
 
 __global__ void __launch_bounds__(SDF_THREADS, SDF_MIN_CTAS)
-k_sdf_dir(SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
+k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SdfSmem& s = *reinterpret_cast<SdfSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool xform = (a.joints != nullptr);
-    const int n_items = (int)w.counters[0];
+    int bucket_end[SDF_BUCKETS];                  // tickets [bucket_end[k-1], bucket_end[k]) belong to bucket k
+    {
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < SDF_BUCKETS; ++k) { run += (int)w.counters[k]; bucket_end[k] = run; }
+    }
+    const int n_items = bucket_end[SDF_BUCKETS - 1];
     float* spill = w.spill + (size_t)blockIdx.x * SDF_SPILL;
 
     for (;;) {
         __syncthreads();                       // the previous item is completely finished
-        if (tid == 0) s.item = (int)atomicAdd(&w.counters[1], 1u);
+        if (tid == 0) s.item = (int)atomicAdd(&w.counters[SDF_BUCKETS], 1u);
         __syncthreads();
         if (s.item >= n_items) break;
-        const uint32_t code = w.items[s.item];
+        uint32_t code;
+        {
+            const int t = s.item;
+            int k = 0, start = 0;
+#pragma unroll
+            for (int q = 0; q + 1 < SDF_BUCKETS; ++q) if (t >= bucket_end[q]) { k = q + 1; start = bucket_end[q]; }
+            code = w.items[(size_t)k * 2 * B + (t - start)];
+        }
         const int b = (int)(code >> 1), h = (int)(code & 1u), o = 1 - h;
         const ushort4* cl_tri = h ? cl_l : cl_r;
         uint16_t* hint = a.hints ? a.hints + ((size_t)b * 2 + h) * SDF_HINTS : nullptr;
@@ -887,11 +911,11 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
         ctas_per_sm = n;
     }
     const SdfWs w = sdf_ws_carve(a.ws, B);
-    IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, 8, st));
+    IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, (SDF_BUCKETS + 1) * 4, st));
     k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, a, w);
     IHMR_LAUNCH_OK();
     const int grid = std::min(std::min(m->num_sms * ctas_per_sm, SDF_MAX_GRID), 2 * B);
-    k_sdf_dir<<<grid, SDF_THREADS, sizeof(SdfSmem), st>>>(a, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
+    k_sdf_dir<<<grid, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
                                                           reinterpret_cast<const ushort4*>(m->cl_tri[1]));
     IHMR_LAUNCH_OK();
     if (a.losses) {
