@@ -92,3 +92,187 @@ class DeviceEvaluator:
     def collision_max(self):
         t, m = self._table()
         return float(np.mean(t[m, 5] * 1000))
+
+
+# ------------------------------------------------------------------------------------------------
+# Host-side records in the reference's own format (result I/O)
+def single_joints_error(pred, gt_xyz, valid, scale):
+    """metric_utils.py:23-38: per-hand root-relative joint errors of the hands whose wrist is annotated (the second
+    hand is measured after BOTH skeletons were already moved to the first wrist, as the reference does in place)."""
+    p, g = np.array(pred, copy=True), np.array(gt_xyz, copy=True)
+    errors = []
+    for i in (0, 21):
+        if valid[i, 0] > 0:
+            p -= p[i:i + 1, :]
+            g -= g[i:i + 1, :]
+            for j in range(21):
+                if valid[i + j, 0] > 0:
+                    errors.append(np.linalg.norm(p[i + j] - g[i + j]) / scale)
+    return errors
+
+
+def single_pa_no_rot_error(pred, gt_xyz, valid, scale):
+    """metric_utils.py:107-143 with use_rot=False: align mean and per-axis spread of the valid joints, no rotation."""
+    v = valid[:, 0] if valid.ndim == 2 else valid
+    if np.sum(v) < 2.0:
+        return []
+    s1, s2 = np.array(pred)[v > 0, :3], np.array(gt_xyz)[v > 0, :3]
+    s1n = (s1 - np.mean(s1, axis=0).reshape(1, 3)) / np.std(s1, axis=0).reshape(1, 3)
+    moved = s1n * np.std(s2, axis=0).reshape(1, 3) + np.mean(s2, axis=0).reshape(1, 3)
+    return (np.linalg.norm(moved - s2, axis=1) / scale).tolist()
+
+
+class Evaluator:
+    """Same constructor, attributes, ``update`` records and summary properties as the reference's ``Evaluator``
+    (/root/reference/src/utils/evaluator.py:20-181) for the refinement driver; ``save`` writes the pickle the reference's
+    own tooling opens (``evaluate_results/optimize/<dataset>.pkl``, src/optimize.py:91-96)."""
+    RECORD_DEFAULTS = dict(annot_type="machine", hand_type="interacting", hand_type_valid=1.0, scale=1.0)
+
+    def __init__(self, opt, test_dataset, model):
+        self.dataset_name = test_dataset.name
+        self.data_list = test_dataset.data_list
+        self.image_root = test_dataset.image_root
+        self.inputSize = model.inputSize
+        self.left_hand_faces = model.mano_models["left"].faces
+        self.right_hand_faces = model.mano_models["right"].faces
+        self.pred_results = list()
+
+    def gather_pred(self, pred_results):
+        self.pred_results += pred_results
+
+    def clear(self):
+        self.pred_results = list()
+
+    def update(self, data_idxs, pred_results, save_verts=True):
+        import os.path as osp
+        self.save_verts = save_verts
+        for i, data_idx in enumerate(data_idxs):
+            data_idx = int(data_idx)
+            src = self.data_list[data_idx]
+            rec = dict(data_idx=data_idx)
+            for k in ("pred_cam_params", "pred_shape_params", "pred_pose_params", "pred_hand_trans", "pred_joints_3d",
+                      "collision_loss_origin_scale", "gt_joints_3d"):
+                rec[k] = np.array(pred_results[k][i])        # owned copies: the flip below edits them in place
+            rec["img_path"] = osp.join(self.image_root, src["img_path"])
+            rec["img_path_relative"] = src["img_path"]
+            for k, dflt in self.RECORD_DEFAULTS.items():
+                rec[k] = src[k] if k in src else dflt
+            if save_verts:
+                for mode in ("pred", "gt"):
+                    for hand in ("left", "right"):
+                        k = f"{mode}_{hand}_hand_verts"
+                        if k in pred_results:
+                            rec[k] = pred_results[k][i].astype(np.float16)
+            gt, valid = rec["gt_joints_3d"][:, :3], rec["gt_joints_3d"][:, 3:]
+            rec["j3d_error"] = single_joints_error(rec["pred_joints_3d"], gt, valid, rec["scale"])
+            rec["pa_no_rot_inter_j3d_error"] = single_pa_no_rot_error(rec["pred_joints_3d"], gt, valid, rec["scale"])
+            if pred_results["do_flip"][i]:
+                self._flip_back(rec)
+            self.pred_results.append(rec)
+
+    def _flip_back(self, rec):
+        """evaluator.py:99-134: undo the left->right mirroring of a flipped sample."""
+        rec["pred_cam_params"][1] *= -1
+        rec["pred_hand_trans"][0] *= -1
+        pose = rec["pred_pose_params"].copy()
+        rec["pred_pose_params"][:48], rec["pred_pose_params"][48:] = pose[48:], pose[:48]
+        rec["pred_pose_params"][1::3] *= -1
+        rec["pred_pose_params"][2::3] *= -1
+        for k in ("pred_joints_3d", "gt_joints_3d"):
+            j = rec[k].copy()
+            rec[k][:21], rec[k][21:] = j[21:], j[:21]
+            rec[k][:, 0] *= -1
+        c = rec["collision_loss_origin_scale"].copy()
+        rec["collision_loss_origin_scale"][:778], rec["collision_loss_origin_scale"][778:] = c[778:], c[:778]
+        if self.save_verts:
+            saved = {k: rec[k].copy() for k in rec if k.endswith("_hand_verts")}
+            for k, v in saved.items():
+                other = k.replace("left", "@").replace("right", "left").replace("@", "right")
+                if other in saved:
+                    rec[k] = saved[other]
+                    rec[k][:, 0] *= -1
+
+    def remove_redunc(self):
+        """evaluator.py:137-146: the dataset is padded to full batches; keep the first record per image."""
+        seen, out = set(), []
+        for rec in self.pred_results:
+            if rec["img_path_relative"] not in seen:
+                out.append(rec)
+                seen.add(rec["img_path_relative"])
+        self.pred_results = out
+
+    @property
+    def mpjpe_3d(self):
+        return np.average([e for r in self.pred_results for e in r["j3d_error"]])
+
+    @property
+    def inter_mpjpe_3d(self):
+        return np.average([e for r in self.pred_results for e in r["pa_no_rot_inter_j3d_error"]])
+
+    @property
+    def collision_ave(self):
+        return np.average([np.mean(r["collision_loss_origin_scale"]) * 1000 for r in self.pred_results
+                           if r["hand_type"] == "interacting"])
+
+    @property
+    def collision_max(self):
+        return np.average([np.max(r["collision_loss_origin_scale"]) * 1000 for r in self.pred_results
+                           if r["hand_type"] == "interacting"])
+
+    # ---- pickle in the reference's format: an instance of `utils.evaluator.Evaluator`
+    def save(self, path):
+        """Writes the file src/optimize.py:91-96 writes: a pickled ``utils.evaluator.Evaluator`` whose attribute
+        dictionary is this object's.  Where the reference's class is importable the file opens as that class; here a
+        stand-in of the same qualified name is registered only while dumping."""
+        import os
+        import pickle
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        with _reference_evaluator_class() as cls:
+            obj = cls.__new__(cls)
+            obj.__dict__.update(self.__dict__)
+            with open(path, "wb") as fh:
+                pickle.dump(obj, fh, protocol=2)
+
+    @classmethod
+    def load(cls, path):
+        import pickle
+        with _reference_evaluator_class():
+            with open(path, "rb") as fh:
+                obj = pickle.load(fh)
+        out = cls.__new__(cls)
+        out.__dict__.update(obj.__dict__)
+        return out
+
+
+class _reference_evaluator_class:
+    """Context: makes `utils.evaluator.Evaluator` resolvable (the real class if the reference is importable,
+    otherwise a bare stand-in that is removed again on exit)."""
+
+    def __enter__(self):
+        import importlib
+        import sys
+        import types
+        self._added = []
+        try:
+            return importlib.import_module("utils.evaluator").Evaluator
+        except Exception:
+            pass
+        for name in ("utils", "utils.evaluator"):
+            if name not in sys.modules:
+                sys.modules[name] = types.ModuleType(name)
+                self._added.append(name)
+        mod = sys.modules["utils.evaluator"]
+        if not hasattr(mod, "Evaluator"):
+            mod.Evaluator = type("Evaluator", (object,), {"__module__": "utils.evaluator"})
+            self._added.append("utils.evaluator:Evaluator")
+        return mod.Evaluator
+
+    def __exit__(self, *exc):
+        import sys
+        for name in reversed(self._added):
+            if name.endswith(":Evaluator"):
+                if "utils.evaluator" in sys.modules and hasattr(sys.modules["utils.evaluator"], "Evaluator"):
+                    delattr(sys.modules["utils.evaluator"], "Evaluator")
+            else:
+                sys.modules.pop(name, None)
+        return False

@@ -480,3 +480,30 @@ def test_camera_gradient_and_stage(model_root, oracle_layers):
     m.run_stage(stage)
     after = m.value_and_grad(stage)[0][0].item()
     assert after <= before * 1.001                        # selection never accepts a worse 2-D loss
+
+
+def test_optimize_dataset_driver_writes_the_reference_result_file(model_root, tmp_path):
+    """The caller side (src/optimize.py:40-102): dataset records -> pipelined refinement -> Evaluator records ->
+    evaluate_results/optimize/<dataset>.pkl, and the records equal what the per-batch calls produce."""
+    from ihmr_b200.evaluator import Evaluator
+    from ihmr_b200.opt_dataset import OPTDataset
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.run_optimize import optimize_dataset
+    from ihmr_b200.strategies import opt_default, with_epochs
+    from tests.test_dataset_io import _write_dataset
+    opt, info = _write_dataset(str(tmp_path), 6)
+    opt.model_root, opt.strategy, opt.save_mid_freq, opt.opt_dataset = model_root, with_epochs(opt_default, 2), 1, "synthetic_ds"
+    out_dir = os.path.join(str(tmp_path), "evaluate_results", "optimize")
+    metrics = optimize_dataset(opt, info, out_dir=out_dir)
+    assert set(metrics) == {"mpjpe_3d", "inter_mpjpe_3d", "collision_ave", "collision_max"} and all(np.isfinite(v) for v in metrics.values())
+    ev = Evaluator.load(os.path.join(out_dir, "synthetic_ds.pkl"))
+    assert len(ev.pred_results) == 6 and [r["data_idx"] for r in ev.pred_results] == list(range(6))
+    ds = OPTDataset(opt, info)
+    ds.load_data()
+    m = OptimizeModel(opt)
+    b0 = next(ds.batches(pin=False))
+    m.set_input(b0); m.init_optimize(); m.optimize(0, 1)
+    res = m.get_pred_result()
+    for i in range(4):
+        assert np.array_equal(ev.pred_results[i]["pred_joints_3d"], res["pred_joints_3d"][i])
+        assert np.array_equal(ev.pred_results[i]["pred_pose_params"], res["pred_pose_params"][i])

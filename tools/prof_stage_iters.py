@@ -2,7 +2,7 @@
 for `ncu --set full`: the second half of each stage's launches is the steady state (hints warm, stage-specialised
 kernels, fingertip-only backward for hands without collision gradient).
 
-    ncu --set full --clock-control none --import-source on -k regex:ihmr -o gpurun_out/r02_full python tools/prof_stage_iters.py
+    ncu --set full --clock-control none --import-source on -k regex:^k_ -o gpurun_out/r02_full python tools/prof_stage_iters.py
 """
 import argparse
 import os
