@@ -99,11 +99,17 @@ struct SdfArgs {
     uint16_t* hints = nullptr;         // (B,2,2048) or null: nearest-face seeds carried from one call to the next on the
                                        // same frames (zeroed by the caller before the first); they change the work, never
                                        // the values
+    int static_grid_mask = 0;          // bit h: hand h's stored vertices are bit-identical in every call since `hints` was
+                                       // zeroed; its column parities / voxel distances are then carried in pcache / phic
+    uint32_t* pcache = nullptr;        // (B, 1056) or null: parity words of 1024 columns + 32 words of "known" bits, zeroed with hints
+    float* phic = nullptr;             // (B, 2048) or null: finished voxel distances beside the hint table (no init needed)
     void* ws = nullptr;                // sdf_ws_bytes(B) of scratch: frame headers, work list, loss parts, spill area
     float* losses = nullptr;           // (B) or null: mask * (part_0 + part_1) / 4 (one more tiny launch)
 };
 size_t sdf_ws_bytes(int B);
 size_t sdf_hint_bytes(int B);
+size_t sdf_pcache_bytes(int B);
+size_t sdf_phic_bytes(int B);
 // (B,2): the sum of rho over the query vertices of each direction of every frame (written by every launch_sdf)
 const float* sdf_ws_parts(void* ws, int B);
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);

@@ -412,6 +412,8 @@ struct OptWs {
     int* take;
     void* sdf_ws;             // scratch of the penetration kernels (sdf_ws_bytes)
     uint16_t* sdf_hints;      // nearest-face seeds the penetration kernel carries from one iteration to the next
+    uint32_t* sdf_pcache;     // static-grid caches of the penetration kernel (stages that move only hand_trans)
+    float* sdf_phic;
     uint8_t* gzero;           // (N) hands whose collision gradient is identically zero this iteration
     int* dense_list;          // (N) the other hands, [N] = their count
 };
@@ -451,6 +453,8 @@ static size_t opt_ws_layout(void* base, int B, OptWs* out) {
     w.shape_cache = (float*)take((size_t)n * NV * 12 * 4);
     w.sdf_ws = take(sdf_ws_bytes(B));
     w.sdf_hints = (uint16_t*)take(sdf_hint_bytes(B));
+    w.sdf_pcache = (uint32_t*)take(sdf_pcache_bytes(B));
+    w.sdf_phic = (float*)take(sdf_phic_bytes(B));
     w.gzero = (uint8_t*)take((size_t)n);
     w.dense_list = (int*)take((size_t)(n + 1) * 4);
     if (out) *out = w;
@@ -511,6 +515,7 @@ struct IterPlan {
                               // carry no gradient, their loss part is needed at snapshots only
     int rigid = 0;            // orientation-only stage: 1 = first iteration (generic forward, then cache the
                               // root-local geometry), 2 = later iterations (x = R0 L + J0); backward is rigid in both
+    bool static_right = false;  // the stage moves only hand_trans: the right hand (grid of the live direction) never changes
     bool dense_grad = false;  // (with IHMR_STAGE_GENERIC_KERNELS) no fingertip-only short path for hands without collision gradient
     int shape = 0;            // shape-only stage: 1 = first iteration (generic forward, then cache T_v | T_v c_v),
                               // 2 = later iterations (affine in beta); backward is the affine one in both
@@ -526,6 +531,7 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot, bool ge
     p.blend_bwd = live_blend;
     p.sdf_skip_grid = (!live_mano && !snapshot) ? 2 : 0;
     p.dense_grad = generic;
+    p.static_right = !live_mano && !generic;
     if (generic) return p;      // IHMR_STAGE_GENERIC_KERNELS: every stage on the generic kernel chain, every hand dense
     if ((mask & (IHMR_P_R_SHAPE | IHMR_P_L_SHAPE)) &&
         !(mask & (IHMR_P_R_POSE | IHMR_P_L_POSE | IHMR_P_R_ORIENT | IHMR_P_L_ORIENT))) {   // opt_default stage 3
@@ -563,7 +569,8 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     IHMR_TICK(prof, 3);
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
-    sa.ws = w.sdf_ws; sa.hints = carry_hints ? w.sdf_hints : nullptr; sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
+    sa.ws = w.sdf_ws; sa.hints = carry_hints ? w.sdf_hints : nullptr;
+    if (carry_hints && plan.static_right) { sa.static_grid_mask = 1; sa.pcache = w.sdf_pcache; sa.phic = w.sdf_phic; } sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
     // generic backward chain: hands without collision gradient take the fingertip-only path (flags from the sdf kernels,
     // list of the others from the loss kernel)
     SparseGrad sp;
@@ -606,6 +613,7 @@ int opt_stage(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr
     IHMR_CUDA_OK(cudaMemsetAsync(w.m, 0, (size_t)B * PD * 4, st));
     IHMR_CUDA_OK(cudaMemsetAsync(w.v, 0, (size_t)B * PD * 4, st));
     IHMR_CUDA_OK(cudaMemsetAsync(w.sdf_hints, 0, sdf_hint_bytes(B), st));
+    IHMR_CUDA_OK(cudaMemsetAsync(w.sdf_pcache, 0, sdf_pcache_bytes(B), st));
     const int nthr = 256, nblk = (int)(((size_t)B * PD + nthr - 1) / nthr);
     int snaps = 0;
     for (int j = 0; j <= stg->epoch; ++j) {
@@ -652,6 +660,7 @@ int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params
     FrameLossArgs la = base_loss_args(B, bs_norm, params, tg, stg, w);
     // one untimed full iteration fills every cached buffer, then the steady-state iteration is timed
     IHMR_CUDA_OK(cudaMemsetAsync(w.sdf_hints, 0, sdf_hint_bytes(B), st));
+    IHMR_CUDA_OK(cudaMemsetAsync(w.sdf_pcache, 0, sdf_pcache_bytes(B), st));
     int rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, nullptr, plan_iteration(stg->update_mask, true, true, stg->flags & IHMR_STAGE_GENERIC_KERNELS), true);
     if (rc) return rc;
     rc = value_and_grad(m, B, bs_norm, params, tg, stg, w, la, st, &prof, plan_iteration(stg->update_mask, false, false, stg->flags & IHMR_STAGE_GENERIC_KERNELS), true);

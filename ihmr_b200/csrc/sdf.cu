@@ -66,6 +66,8 @@ static_assert(PHI_CAP <= 65536 && TV <= 32 && V_CHUNK >= TV, "queue entries pack
 constexpr int SDF_SPILL = NV * 8;   // a direction evaluates at most 8 voxels per query vertex
 constexpr int SDF_MAX_GRID = 160 * 8;
 constexpr int SDF_HINTS = 2048;     // nearest-face hints per (frame, direction): one u16 per voxel of an 8 x 16 x 16 block (wraps)
+constexpr uint32_t HINT_DONE = 0xffffffffu, HINT_NONE = 0xfffffffeu;   // states of a voxel in hintw (else: seed slot)
+constexpr int SDF_PCACHE = G * G + G;   // words per frame of the static-grid parity cache: 1024 columns + 32 words of "known" bits
 constexpr int SDF_HDR = 40;         // floats per frame header (see k_sdf_prep)
 constexpr float Q8_TO_D2 = 1.0f / 16384.0f;         // Q8 units squared -> normalised units squared
 constexpr float Q4D2_TO_D2 = 0.25f * Q8_TO_D2;      // qbox_4d2 units -> normalised units squared
@@ -430,6 +432,8 @@ __global__ void k_sdf_finish(int B, const float* __restrict__ parts, const float
 // place (queue full), [16+h] direction finished by k_sdf_prep, [19..27] cycles per phase (mark, face boxes,
 // parity, scan, worklist, seeds + candidates, exact tests, finish, sample + outputs)
 
+// kStatic = false compiles the static-grid cache out (stages in which both hands move)
+template <bool kStatic>
 __global__ void __launch_bounds__(SDF_THREADS, SDF_MIN_CTAS)
 k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -567,7 +571,14 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
         }
         SDF_STAT(1)
         int total = 0;
-        if (any_block) {
+        // Static grid (a stage that moves only hand_trans: the right hand is bit-identical over the whole stage):
+        // column parities and finished voxel distances of this frame are carried in HBM from one iteration to the
+        // next, so only newly touched columns / voxels need the grid hand's geometry at all.
+        const bool stat = kStatic && ((a.static_grid_mask >> h) & 1);
+        uint32_t* pcw = stat ? a.pcache + (size_t)b * SDF_PCACHE : nullptr;      // [1024] parity words, [32] known bits
+        float* phic = stat ? a.phic + (size_t)b * SDF_HINTS : nullptr;
+        bool geom_ready = false;
+        auto geometry = [&]() {          // block-uniform: U, face boxes, cluster boxes (ends with a barrier)
             // ---- normalised grid-hand vertices
             for (int v = tid; v < NV; v += SDF_THREADS) {
                 float p[3];
@@ -604,6 +615,25 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                                              (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16));
             }
             __syncthreads();
+            geom_ready = true;
+        };
+        if (any_block) {
+            // which marked columns still need their parity: all of them, or (static grid) those not known yet
+            bool any_new = true;
+            if (stat) {
+                bool mynew = false;
+                for (int c = tid; c < G * G; c += SDF_THREADS) {
+                    uint16_t flag = 0;
+                    if (s.needed[c]) {
+                        if ((pcw[G * G + (c >> 5)] >> (c & 31)) & 1u) s.work[c] = pcw[c];
+                        else { flag = 1; mynew = true; }
+                    }
+                    s.coloff[c] = flag;      // (coloff is free until the scan)
+                }
+                any_new = __syncthreads_or(mynew);
+            }
+            if (any_new) {
+            geometry();
             SDF_STAT(2)
             // ---- parity of the marked columns, two steps so that the ray tests run with full warps:
             //      (1) thread per face: lattice points inside its (y,z) box whose column is marked
@@ -656,7 +686,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
 #pragma unroll
                     for (int dj = 0; dj < 2; ++dj) {
                         const int k = k0 + dk, j = j0 + dj, col = k * G + j;
-                        push(small && k <= k1 && j <= j1 && s.needed[col & (G * G - 1)] != 0u, slot, col);
+                        push(small && k <= k1 && j <= j1 && (stat ? s.coloff[col & (G * G - 1)] != 0 : s.needed[col & (G * G - 1)] != 0u), slot, col);
                     }
                 uint32_t bigm = __ballot_sync(0xffffffffu, cover && !small);
                 while (bigm) {
@@ -668,7 +698,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                     const int nj = fj1 - fj0 + 1, npts = nj * (fk1 - fk0 + 1);
                     for (int t0 = 0; t0 < npts; t0 += 32) {
                         const int t = t0 + lane, dk = t / nj, col = (fk0 + dk) * G + fj0 + (t - dk * nj);
-                        push(t < npts && s.needed[col & (G * G - 1)] != 0u, ff, col);
+                        push(t < npts && (stat ? s.coloff[col & (G * G - 1)] != 0 : s.needed[col & (G * G - 1)] != 0u), ff, col);
                     }
                 }
             }
@@ -677,6 +707,12 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             __syncthreads();
             for_each_queued([&](uint32_t e) { ray_item((int)(e >> 10), (int)(e & 1023u)); });
             __syncthreads();
+            if (stat) {                  // the new columns' parity words are known from now on
+                for (int c = tid; c < G * G; c += SDF_THREADS)
+                    if (s.coloff[c]) { pcw[c] = s.work[c]; atomicOr(&pcw[G * G + (c >> 5)], 1u << (c & 31)); }
+                __syncthreads();         // (coloff is rewritten by the scan below)
+            }
+            }   // any_new
             SDF_STAT(3)
             // ---- marked & inside, prefix offsets
             int cnt[SDF_CPT], excl[SDF_CPT];
@@ -716,7 +752,32 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                 }
             }
             __syncthreads();
-            if (a.stats && tid == 0) { atomicAdd(&a.stats[b * 32 + 2 * h], nvox); atomicAdd(&a.stats[b * 32 + 10], 1); }
+            // ---- static grid: what is known about each voxel from the previous iterations — its finished distance, or
+            //      at least its nearest face (a seed)
+            bool any_todo = true;
+            int nhit = 0;
+            if (stat) {
+                bool mytodo = false;
+                for (int i = tid; i < nvox; i += SDF_THREADS) {
+                    uint32_t state = HINT_NONE;
+                    const uint32_t q = s.worklist[i];
+                    const int hi_ = hint_index(q);
+                    const uint32_t e = hint[hi_];
+                    if (((e >> 11) & 15u) == hint_tag(q) && (e & 2047u)) {
+                        if (e & 0x8000u) { state = HINT_DONE; s.best[i] = __float_as_uint(phic[hi_]); ++nhit; }
+                        else state = (e & 2047u) - 1u;
+                    }
+                    s.hintw[i] = state;
+                    mytodo = mytodo || state != HINT_DONE;
+                }
+                any_todo = __syncthreads_or(mytodo);
+                if (any_todo && !geom_ready) geometry();
+            }
+            if (a.stats) {
+                nhit = __reduce_add_sync(0xffffffffu, nhit);
+                if (lane == 0 && nhit) atomicAdd(&a.stats[b * 32 + 13], nhit);
+                if (tid == 0) { atomicAdd(&a.stats[b * 32 + 2 * h], nvox); atomicAdd(&a.stats[b * 32 + 10], 1); }
+            }
             SDF_STAT(5)
             // ---- nearest face of every voxel.  Rounds of V_CHUNK voxels:
             //   (S) warp per voxel, TV voxels at a time: distances to the NCL cluster boxes -> nearest cluster ->
@@ -726,19 +787,26 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             //       face boxes, so it is never farther than any of them) -> their faces whose box is closer than
             //       best -> (voxel, face) candidates.  A face that fails either test cannot be nearer than best.
             //   (C) thread per candidate: exact point-triangle test, atomicMin into the voxel
-            for (int v0 = 0; v0 < nvox; v0 += V_CHUNK) {
+            for (int v0 = 0; v0 < nvox && any_todo; v0 += V_CHUNK) {
                 const int v1 = min(nvox, v0 + V_CHUNK);
                 uint32_t* wqueue = s.queue + warp * QSEG;      // candidates of this warp's voxels: no atomics
                 int wq = 0, ncand = 0;                           // fill (warp-uniform), candidates found
                 for (int t0 = v0 + warp * TV; t0 < v1; t0 += SDF_WARPS * TV) {
                     const int nt = min(TV, v1 - t0);
-                    // seeds carried over from the previous iteration of the refinement loop
                     int myseed = -1;
-                    if (hint && lane < nt) {
-                        const uint32_t q = s.worklist[t0 + lane], e = hint[hint_index(q)];
-                        if ((e >> 11) == hint_tag(q)) myseed = (int)(e & 2047u) - 1;
+                    bool mydone = false;
+                    if (lane < nt) {
+                        if (stat) {
+                            const uint32_t st_ = s.hintw[t0 + lane];
+                            mydone = st_ == HINT_DONE;
+                            if (st_ < HINT_NONE) myseed = (int)st_;
+                        } else if (hint) {       // seeds carried over from the previous iteration of the refinement loop
+                            const uint32_t q = s.worklist[t0 + lane], e = hint[hint_index(q)];
+                            if (((e >> 11) & 15u) == hint_tag(q)) myseed = (int)(e & 2047u) - 1;
+                        }
                     }
-                    const uint32_t have = __ballot_sync(0xffffffffu, myseed >= 0);
+                    const uint32_t have = __ballot_sync(0xffffffffu, myseed >= 0 || mydone);       // no seed search needed
+                    const uint32_t todo = __ballot_sync(0xffffffffu, lane < nt && !mydone);
                     for (int k = 0; k < nt; ++k) {
                         if ((have >> k) & 1u) continue;
                         const uint32_t q = s.worklist[t0 + k];
@@ -764,12 +832,13 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                         kf = __reduce_min_sync(0xffffffffu, kf);
                         if (lane == k) myseed = (int)(kf & 2047u);
                     }
-                    if (lane < nt) {
+                    if (lane < nt && !mydone) {
                         s.best[t0 + lane] = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[t0 + lane], myseed));
                         s.hintw[t0 + lane] = (uint32_t)myseed;
                     }
                     __syncwarp();
                     for (int k = 0; k < nt; ++k) {
+                        if (!((todo >> k) & 1u)) continue;
                         const int v = t0 + k;
                         const uint32_t q = s.worklist[v];
                         const float bv = __uint_as_float(s.best[v]);
@@ -810,10 +879,18 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             }
             // ---- phi = distance
             for (int i = tid; i < nvox; i += SDF_THREADS) {
-                const float d = sqrtf(__uint_as_float(s.best[i]));
-                s.best[i] = __float_as_uint(d);
+                float d = __uint_as_float(s.best[i]);
+                if (!stat || s.hintw[i] != HINT_DONE) {              // (known voxels already hold the distance)
+                    d = sqrtf(d);
+                    s.best[i] = __float_as_uint(d);
+                    if (hint) {
+                        const uint32_t q = s.worklist[i];
+                        const int hi_ = hint_index(q);
+                        hint[hi_] = (uint16_t)((stat ? 0x8000u : 0u) | (hint_tag(q) << 11) | (s.hintw[i] + 1u));
+                        if (stat) phic[hi_] = d;
+                    }
+                }
                 if (multi) spill[pass0 + i] = d;
-                if (hint) hint[hint_index(s.worklist[i])] = (uint16_t)((hint_tag(s.worklist[i]) << 11) | (uint32_t)(s.hintw[i] + 1));
             }
             __syncthreads();
             SDF_STAT(8)
@@ -901,22 +978,24 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     if (B <= 0) return IHMR_OK;
     if (!a.ws) { set_error("sdf: no workspace"); return IHMR_E_INVALID; }
-    static unsigned long long configured = 0ull;
-    static int ctas_per_sm = 0;
-    if (int rc = ensure_dynamic_smem(k_sdf_dir, sizeof(SdfSmem), configured)) return rc;
-    if (ctas_per_sm == 0) {
+    static unsigned long long configured[2] = {0ull, 0ull};
+    static int ctas_per_sm[2] = {0, 0};
+    const bool use_static = a.static_grid_mask && a.pcache && a.phic && a.hints;
+    auto kernel = use_static ? k_sdf_dir<true> : k_sdf_dir<false>;
+    if (int rc = ensure_dynamic_smem(kernel, sizeof(SdfSmem), configured[use_static])) return rc;
+    if (ctas_per_sm[use_static] == 0) {
         int n = 0;
-        IHMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sdf_dir, SDF_THREADS, sizeof(SdfSmem)));
+        IHMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, SDF_THREADS, sizeof(SdfSmem)));
         if (n < 1) { set_error("sdf: the kernel does not fit on an SM"); return IHMR_E_CUDA; }
-        ctas_per_sm = n;
+        ctas_per_sm[use_static] = n;
     }
     const SdfWs w = sdf_ws_carve(a.ws, B);
     IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, (SDF_BUCKETS + 1) * 4, st));
     k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, a, w);
     IHMR_LAUNCH_OK();
-    const int grid = std::min(std::min(m->num_sms * ctas_per_sm, SDF_MAX_GRID), 2 * B);
-    k_sdf_dir<<<grid, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
-                                                          reinterpret_cast<const ushort4*>(m->cl_tri[1]));
+    const int grid = std::min(std::min(m->num_sms * ctas_per_sm[use_static], SDF_MAX_GRID), 2 * B);
+    kernel<<<grid, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
+                                                       reinterpret_cast<const ushort4*>(m->cl_tri[1]));
     IHMR_LAUNCH_OK();
     if (a.losses) {
         k_sdf_finish<<<(B + 255) / 256, 256, 0, st>>>(B, w.parts, a.hand_type, a.losses);
@@ -925,6 +1004,8 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     return IHMR_OK;
 }
 
+size_t sdf_pcache_bytes(int B) { return (size_t)B * SDF_PCACHE * sizeof(uint32_t); }
+size_t sdf_phic_bytes(int B) { return (size_t)B * SDF_HINTS * sizeof(float); }
 size_t sdf_hint_bytes(int B) { return (size_t)B * 2 * SDF_HINTS * sizeof(uint16_t); }
 
 const float* sdf_ws_parts(void* ws, int B) { return sdf_ws_carve(ws, B).parts; }
