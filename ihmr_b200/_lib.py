@@ -15,7 +15,7 @@ EXPORTS = (
     "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",
     "ihmr_model_update_shapedirs", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
     "ihmr_mano_backward", "ihmr_sdf_workspace_bytes", "ihmr_sdf_loss", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
-    "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics", "ihmr_measure_fp32_peak", "ihmr_select_snapshots",
+    "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics", "ihmr_measure_fp32_peak", "ihmr_select_snapshots", "ihmr_opt_criteria", "ihmr_mlp_input", "ihmr_linear", "ihmr_mlp_apply", "ihmr_select_better",
 )
 KERNEL_CLASSES = ("pose_prep", "blend_fwd", "skin_fwd", "sdf", "frame_loss", "skin_bwd", "blend_bwd", "pose_bwd", "step")
 
@@ -99,6 +99,16 @@ def load() -> C.CDLL:
         fn.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
     lib.ihmr_eval_metrics.restype = i32
     lib.ihmr_eval_metrics.argtypes = [i32, vp, vp, vp, vp, vp, vp]
+    lib.ihmr_opt_criteria.restype = i32
+    lib.ihmr_opt_criteria.argtypes = [vp, i32, vp, C.POINTER(Targets), f32, f32, vp, vp, sz, vp]
+    lib.ihmr_mlp_input.restype = i32
+    lib.ihmr_mlp_input.argtypes = [i32, vp, vp, vp, vp]
+    lib.ihmr_linear.restype = i32
+    lib.ihmr_linear.argtypes = [i32, i32, i32, vp, i32, vp, vp, i32, vp, i32, vp]
+    lib.ihmr_mlp_apply.restype = i32
+    lib.ihmr_mlp_apply.argtypes = [i32, vp, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, vp, vp]
+    lib.ihmr_select_better.restype = i32
+    lib.ihmr_select_better.argtypes = [i32, vp, vp, C.POINTER(Stage), vp, vp, vp, vp]
     lib.ihmr_select_snapshots.restype = i32
     lib.ihmr_select_snapshots.argtypes = [i32, i32, vp, C.POINTER(Stage), vp, vp]
     lib.ihmr_measure_fp32_peak.restype = i32

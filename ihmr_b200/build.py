@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libihmr_b200.so")
-SOURCES = ["abi.cu", "mano.cu", "sdf.cu", "opt.cu", "blend_tc.cu", "eval.cu"]
+SOURCES = ["abi.cu", "mano.cu", "sdf.cu", "opt.cu", "blend_tc.cu", "eval.cu", "mlp.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "ihmr_b200.h")]
 
 # Extra libraries for the tests: name -> (path, source recompiled with extra flags).  `smallcaps` shrinks the shared-memory

@@ -33,6 +33,8 @@ int opt_final(const ihmr_model* m, int B, const float* params, const ihmr_target
 int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr_targets_t* tg,
                           const ihmr_stage_t* stg, float* ms, void* ws, cudaStream_t st);
 int select_snapshots(int S, int B, const float* crit, const ihmr_stage_t* stg, int* index, cudaStream_t st);
+int opt_criteria(const ihmr_model* m, int B, const float* params, const ihmr_targets_t* tg, float w_joints_2d, float w_joints_3d,
+                 float* criteria, void* ws, cudaStream_t st);
 
 template <typename T>
 static int upload(T** dst, const std::vector<T>& host) {
@@ -318,14 +320,6 @@ int ihmr_eval_metrics(int n_frames, const float* pred_joints_3d, const float* gt
     return launch_eval_metrics(n_frames, pred_joints_3d, gt_joints_3d, collision_origin_scale, scale, out, static_cast<cudaStream_t>(stream));
 }
 
-int ihmr_measure_fp32_peak(const ihmr_model_t* m, float* tflops, void* scratch, ihmr_stream_t stream) {
-    IHMR_CHECK_ARG(m && tflops && scratch);
-    DeviceGuard guard(m->device);
-    return measure_fp32_peak(m->num_sms, tflops, static_cast<float*>(scratch), static_cast<cudaStream_t>(stream));
-}
-
-size_t ihmr_opt_workspace_bytes(int n_frames) { return n_frames > 0 ? opt_ws_bytes(n_frames) : 0; }
-
 static int check_targets(const ihmr_targets_t* t) {
     IHMR_CHECK_ARG(t && t->init_joints_2d && t->init_joints_3d && t->init_hand_trans_j && t->gt_joints_3d && t->hand_type_array);
     return IHMR_OK;
@@ -337,6 +331,43 @@ static int check_stage(const ihmr_stage_t* s) {
     for (int f = 0; f < s->n_filters; ++f) IHMR_CHECK_ARG(s->filter_loss[f] >= 0 && s->filter_loss[f] <= 2);
     return IHMR_OK;
 }
+
+int ihmr_mlp_input(int n, const float* img_feat, const float* params, float* x, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(n >= 0 && img_feat && params && x);
+    return launch_mlp_input(n, img_feat, params, x, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_linear(int n, int in_dim, int out_dim, const float* x, int ldx, const float* weight, const float* bias, int relu,
+                float* y, int ldy, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(n >= 0 && x && weight && y && in_dim > 0 && out_dim > 0 && in_dim % 32 == 0 && ldx % 4 == 0 && ldy % 4 == 0);
+    IHMR_CHECK_ARG(ldx >= in_dim && ldy >= ((out_dim + 3) & ~3));
+    return launch_linear(n, in_dim, out_dim, x, ldx, weight, bias, relu, y, ldy, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_mlp_apply(int n, const float* residual, int ldr, int n_segments, const int32_t* seg_col, const int32_t* seg_len,
+                   const float* params_in, float* params_out, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(n >= 0 && residual && params_in && params_out && n_segments >= 0 && n_segments <= 8 && (n_segments == 0 || (seg_col && seg_len)));
+    int tot = 0;
+    for (int i = 0; i < n_segments; ++i) { IHMR_CHECK_ARG(seg_col[i] >= 0 && seg_len[i] > 0 && seg_col[i] + seg_len[i] <= IHMR_PARAM_DIM); tot += seg_len[i]; }
+    IHMR_CHECK_ARG(tot <= ldr);
+    return launch_mlp_apply(n, residual, ldr, n_segments, seg_col, seg_len, params_in, params_out, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_select_better(int n, const float* cur_criteria, float* prev_criteria, const ihmr_stage_t* stage, const float* new_params,
+                       float* params, int32_t* kept, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(n >= 0 && cur_criteria && prev_criteria && new_params && params);
+    int rc;
+    if ((rc = check_stage(stage))) return rc;
+    return launch_select_better(n, cur_criteria, prev_criteria, stage, new_params, params, kept, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_measure_fp32_peak(const ihmr_model_t* m, float* tflops, void* scratch, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && tflops && scratch);
+    DeviceGuard guard(m->device);
+    return measure_fp32_peak(m->num_sms, tflops, static_cast<float*>(scratch), static_cast<cudaStream_t>(stream));
+}
+
+size_t ihmr_opt_workspace_bytes(int n_frames) { return n_frames > 0 ? opt_ws_bytes(n_frames) : 0; }
 
 int ihmr_opt_stage(const ihmr_model_t* m, int B, int bs_norm, float* params, const ihmr_targets_t* targets,
                    const ihmr_stage_t* stage, int save_mid_freq, int optimizer, void* workspace,
@@ -361,6 +392,16 @@ int ihmr_opt_final(const ihmr_model_t* m, int B, const float* params, const ihmr
     DeviceGuard guard(m->device);
     return opt_final(m, B, params, targets, right_verts, left_verts, joints_3d, collision_loss,
                      collision_origin_scale, joints_3d_loss_p, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int ihmr_opt_criteria(const ihmr_model_t* m, int B, const float* params, const ihmr_targets_t* targets, float w_joints_2d,
+                      float w_joints_3d, float* criteria, void* workspace, size_t workspace_bytes, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && B > 0 && params && workspace && criteria);
+    int rc;
+    if ((rc = check_targets(targets))) return rc;
+    if (workspace_bytes < opt_ws_bytes(B)) { set_error("workspace too small: %zu < %zu", workspace_bytes, opt_ws_bytes(B)); return IHMR_E_WORKSPACE; }
+    DeviceGuard guard(m->device);
+    return opt_criteria(m, B, params, targets, w_joints_2d, w_joints_3d, criteria, workspace, static_cast<cudaStream_t>(stream));
 }
 
 int ihmr_opt_value_and_grad(const ihmr_model_t* m, int B, int bs_norm, const float* params,

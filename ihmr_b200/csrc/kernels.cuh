@@ -118,6 +118,15 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
 int launch_eval_metrics(int B, const float* pred, const float* gt, const float* origin, const float* scale, float* out,
                         cudaStream_t st);
 
+// IHMR-MLP inference pieces (mlp.cu)
+int launch_mlp_input(int n, const float* feat, const float* params, float* x, cudaStream_t st);
+int launch_linear(int n, int in_dim, int out_dim, const float* x, int ldx, const float* W, const float* bias, int relu,
+                  float* y, int ldy, cudaStream_t st);
+int launch_mlp_apply(int n, const float* res, int ldr, int n_seg, const int* col, const int* len, const float* pin, float* pout,
+                     cudaStream_t st);
+int launch_select_better(int n, const float* cur, float* prev, const ihmr_stage_t* stg, const float* pnew, float* params, int* kept,
+                         cudaStream_t st);
+
 // FP32 FMA throughput of the device in TFLOP/s (synchronises the stream; scratch: >= 4 bytes of device memory)
 int measure_fp32_peak(int num_sms, float* tflops, float* scratch, cudaStream_t st);
 

@@ -31,6 +31,7 @@ struct FrameLossArgs {
     float* j2d_batch;             // (B) joints_2d_loss_p_batch, or null
     float* j3d_batch;             // (B) joints_3d_loss_p_batch, or null
     float* joints_out;            // (B,42,3) root-aligned joints, or null
+    float* crit3;                 // (B,3) [joints_3d_loss_p, collision_loss, joints_2d_loss_p] (IHMR_LOSS_* order), or null
     // online snapshot selection
     int snap_mode;                // 0 none, 1 first snapshot of the stage, 2 later snapshot
     int n_filters;
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_frame_loss(FrameLossArgs a) {
             const float* ht = a.tg.hand_type_array + (size_t)b * 2;
             col = ((ht[0] + ht[1] > 1.5f) ? 1.0f : 0.0f) * (a.col_parts[b * 2] + a.col_parts[b * 2 + 1]) * 0.25f;
         }
+        if (a.crit3) { a.crit3[b * 3] = j3d_b; a.crit3[b * 3 + 1] = col; a.crit3[b * 3 + 2] = j2d_b; }
         if (a.j2d_batch) a.j2d_batch[b] = j2d_b;
         if (a.j3d_batch) a.j3d_batch[b] = j3d_b;
         if (a.loss_parts) {
@@ -692,6 +694,28 @@ int opt_value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* par
         IHMR_LAUNCH_OK();
     }
     if (grad) IHMR_CUDA_OK(cudaMemcpyAsync(grad, w.grad, (size_t)B * PD * 4, cudaMemcpyDeviceToDevice, st));
+    return IHMR_OK;
+}
+
+// forward + the three per-frame selection criteria, nothing else (IHMR-MLP inference, mlp_model.py:514-583 as far as
+// select_better_params reads it): joints_3d_loss_p and joints_2d_loss_p carry their weights, collision_loss weight 1
+int opt_criteria(const ihmr_model* m, int B, const float* params, const ihmr_targets_t* tg, float w_joints_2d, float w_joints_3d,
+                 float* criteria, void* ws, cudaStream_t st) {
+    OptWs w;
+    opt_ws_layout(ws, B, &w);
+    int rc;
+    if ((rc = forward_all(m, B, params, w, st))) return rc;
+    SdfArgs sa;
+    sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
+    sa.losses = w.col_loss; sa.ws = w.sdf_ws;
+    if ((rc = launch_sdf(m, B, sa, st))) return rc;
+    ihmr_stage_t wts{};
+    wts.w_joints_2d = w_joints_2d; wts.w_joints_3d = w_joints_3d;
+    FrameLossArgs la = base_loss_args(B, B, params, tg, &wts, w);
+    la.col_loss = w.col_loss;
+    la.crit3 = criteria;
+    k_frame_loss<<<B, FL_THREADS, 0, st>>>(la);
+    IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
 

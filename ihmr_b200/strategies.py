@@ -41,4 +41,23 @@ def with_epochs(strategy: List[dict], epoch: int) -> List[dict]:
     return out
 
 
-strategies: Dict[str, List[dict]] = dict(opt_default=opt_default, opt_fixed100=with_epochs(opt_default, 24))
+# IHMR-MLP (src/strategies/mlp_default.py): what the test-time path reads of each stage — which parameters the stage's
+# residual MLP proposes, and the criteria select_better_params compares (mlp_model.py:592-637).  Training-only fields
+# (loss weights, lr schedule, epochs) are not part of inference.
+_MLP_F = [("joints_3d_loss_p", "+0"), ("collision_loss", "+0")]
+
+
+def _mlp_stage(update_params, filter_loss=None, select_loss="collision_loss") -> dict:
+    return dict(update_params=list(update_params), filter_loss=list(filter_loss or _MLP_F), select_loss=select_loss)
+
+
+mlp_default: List[dict] = [
+    _mlp_stage(["pred_hand_trans"]),
+    _mlp_stage(["pred_left_orient"]),
+    _mlp_stage(["pred_right_orient"]),
+    _mlp_stage(["pred_left_pose_params", "pred_right_pose_params"]),
+    _mlp_stage(["pred_left_shape_params", "pred_right_shape_params"]),
+    _mlp_stage(["pred_cam_params"], [("joints_2d_loss_p", "+0")], "joints_2d_loss_p"),
+]
+
+strategies: Dict[str, List[dict]] = dict(opt_default=opt_default, opt_fixed100=with_epochs(opt_default, 24), mlp_default=mlp_default)

@@ -189,6 +189,34 @@ int ihmr_opt_value_and_grad(const ihmr_model_t* model, int n_frames, int bs_norm
 int ihmr_select_snapshots(int n_snapshots, int n_frames, const float* criteria, const ihmr_stage_t* stage,
                           int32_t* index, ihmr_stream_t stream);
 
+/* ---- IHMR-MLP inference ------------------------------------------
+ * The test-time path of src/models/mlp_model.py:683-699: per strategy stage a residual MLP
+ * (src/models/networks.py:83-105, InterHandSubNetwork) proposes new values for the stage's parameters from
+ * [image feature 1024 | final_params 122], the MANO forward + criteria are evaluated (ihmr_opt_final), and
+ * select_better_params (:592-637) keeps the proposal per frame only where the criteria improved.
+ * ihmr_mlp_input: x (n,1152) = [img_feat (n,1024) | cam, pose, shape, hand_trans in the reference's final_params order
+ *   (:432-436) taken from params (n,122) in this library's order | zeros].
+ * ihmr_linear: y[:, :out_dim] = act(x (n,in_dim) . weight^T + bias), weight (ceil4(out_dim), in_dim) row-major = the
+ *   nn.Linear layout with the rows padded to a multiple of 4 (zeros), in_dim % 32 == 0; relu != 0 applies ReLU.
+ * ihmr_mlp_apply: params_out = params_in + residual on the listed column segments of the (n,122) matrix; residual
+ *   columns are consumed in list order (the order of stage['update_params'], :462-470).
+ * ihmr_select_better: per frame, new_params replace params on the stage's update groups and cur_criteria replace
+ *   prev_criteria (n,3: IHMR_LOSS_* order) iff cur[f] < prev[f] * (1 + percent_f / 100) for every filter and
+ *   cur[select] <= prev[select]; kept (n) [may be NULL] receives 1 / 0.
+ * ihmr_opt_criteria: forward of params (n,122) and the three per-frame criteria (n,3) = [joints_3d_loss_p * w_joints_3d,
+ *   collision_loss, joints_2d_loss_p * w_joints_2d] (what compute_loss leaves in the *_batch attributes select_better_params
+ *   reads, :525-538,578-582); workspace as for ihmr_opt_stage. */
+int ihmr_opt_criteria(const ihmr_model_t* model, int n_frames, const float* params, const ihmr_targets_t* targets,
+                      float w_joints_2d, float w_joints_3d, float* criteria, void* workspace, size_t workspace_bytes,
+                      ihmr_stream_t stream);
+int ihmr_mlp_input(int n, const float* img_feat, const float* params, float* x, ihmr_stream_t stream);
+int ihmr_linear(int n, int in_dim, int out_dim, const float* x, int ldx, const float* weight, const float* bias, int relu,
+                float* y, int ldy, ihmr_stream_t stream);
+int ihmr_mlp_apply(int n, const float* residual, int ldr, int n_segments, const int32_t* seg_col, const int32_t* seg_len,
+                   const float* params_in, float* params_out, ihmr_stream_t stream);
+int ihmr_select_better(int n, const float* cur_criteria, float* prev_criteria, const ihmr_stage_t* stage,
+                       const float* new_params, float* params, int32_t* kept, ihmr_stream_t stream);
+
 /* ---- evaluator metrics on the device ------------------------------
  * Replaces the host-side per-frame metric code the reference runs after get_pred_result:
  * mu.get_single_joints_error and mu.get_single_pa_inter_joints_error(use_rot=False)
