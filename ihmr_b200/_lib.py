@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("IHMR_B200_LIB", os.path.join(_HERE, "_lib", "libihmr_
 EXPORTS = (
     "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",
     "ihmr_model_update_shapedirs", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
-    "ihmr_mano_backward", "ihmr_sdf_workspace_bytes", "ihmr_sdf_loss", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
+    "ihmr_mano_backward", "ihmr_sdf_workspace_bytes", "ihmr_sdf_loss", "ihmr_sdf_loss_exact", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
     "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics", "ihmr_measure_fp32_peak", "ihmr_select_snapshots", "ihmr_opt_criteria", "ihmr_mlp_input", "ihmr_linear", "ihmr_mlp_apply", "ihmr_select_better",
 )
 KERNEL_CLASSES = ("pose_prep", "blend_fwd", "skin_fwd", "sdf", "frame_loss", "skin_bwd", "blend_bwd", "pose_bwd", "step")
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     lib.ihmr_sdf_workspace_bytes.argtypes = [i32]
     lib.ihmr_sdf_loss.restype = i32
     lib.ihmr_sdf_loss.argtypes = [vp, i32, vp, vp, vp, vp, vp, f32, vp, sz, vp]
+    lib.ihmr_sdf_loss_exact.restype = i32
+    lib.ihmr_sdf_loss_exact.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ihmr_opt_workspace_bytes.restype = sz
     lib.ihmr_opt_workspace_bytes.argtypes = [i32]
     lib.ihmr_opt_stage.restype = i32

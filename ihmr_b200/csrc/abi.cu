@@ -304,6 +304,17 @@ int ihmr_sdf_loss(const ihmr_model_t* m, int n_frames, const float* hand_verts, 
     return launch_sdf(m, n_frames, a, static_cast<cudaStream_t>(stream));
 }
 
+int ihmr_sdf_loss_exact(const ihmr_model_t* m, int n_frames, const float* hand_verts, float* losses, float* per_vert,
+                        float* origin_scale, float* grad_hand_verts, void* workspace, size_t workspace_bytes, ihmr_stream_t stream) {
+    IHMR_CHECK_ARG(m && n_frames >= 0 && hand_verts && losses && (workspace || n_frames == 0));
+    if (workspace_bytes < ihmr_sdf_workspace_bytes(n_frames)) { set_error("workspace too small: %zu < %zu", workspace_bytes, ihmr_sdf_workspace_bytes(n_frames)); return IHMR_E_WORKSPACE; }
+    DeviceGuard guard(m->device);
+    SdfArgs a;
+    a.verts = hand_verts; a.losses = losses; a.per_vert = per_vert; a.origin = origin_scale;
+    a.gverts = grad_hand_verts; a.ws = workspace;
+    return launch_sdf_exact(m, n_frames, a, static_cast<cudaStream_t>(stream));
+}
+
 int ihmr_sdf_stats(const ihmr_model_t* m, int n_frames, const float* hand_verts, float* losses, int* stats,
                    void* workspace, size_t workspace_bytes, ihmr_stream_t stream) {
     IHMR_CHECK_ARG(m && n_frames >= 0 && hand_verts && losses && stats && (workspace || n_frames == 0));

@@ -113,6 +113,8 @@ size_t sdf_phic_bytes(int B);
 // (B,2): the sum of rho over the query vertices of each direction of every frame (written by every launch_sdf)
 const float* sdf_ws_parts(void* ws, int B);
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
+// the exact (grid-free) mode: same arguments and outputs, different function (see sdf.cu); hints / caches are not used
+int launch_sdf_exact(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st);
 
 // per-frame evaluator metrics (eval.cu): out (B,6)
 int launch_eval_metrics(int B, const float* pred, const float* gt, const float* origin, const float* scale, float* out,

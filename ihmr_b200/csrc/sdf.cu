@@ -975,6 +975,268 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
     }
 }
 
+// =========================================================================================================
+// EXACT (grid-free) penetration mode — SURVEY.md §8(f) rank 3.  NOT the reference's function: a separately named
+// alternative to the 32^3 field.  For every query vertex p (normalised by the grid hand's box as in Appendix B):
+//     psi = dist(p, mesh_h) if p is inside mesh_h (odd number of +x ray crossings) else 0
+// i.e. the limit of the reference's field for an infinitely fine grid: no 7 mm voxel quantisation, and per direction
+// at most 778 inside tests and distance searches instead of up to 8 voxels per vertex.  Same work list, boxes and
+// loss conventions as the grid mode (loss = sum psi / 4, origin_scale = psi * scale, gradient to the query vertex only).
+// One CTA per (frame, direction); a warp owns a vertex for the inside test and for the nearest-face search.
+struct __align__(16) SdfExactSmem {
+    float U[NV * 3];
+    uint2 cl_box[NCL];
+    uint2 fbox[NCL * 32];
+    float4 act[NV];             // active query vertices: normalised position, vertex id (as bits)
+    float4 outv[NV];            // per query vertex: psi, gradient direction d psi / d p
+    float red[4 * SDF_WARPS];
+    int nact, item;
+};
+
+// closest point of triangle (a,b,c) to p (Ericson, Real-Time Collision Detection 5.1.5)
+__device__ __forceinline__ void pt_tri_closest(const float* p, const float* a, const float* b, const float* c, float* out) {
+    float ab[3], ac[3], ap[3], bp[3], cp[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; bp[k] = p[k] - b[k]; cp[k] = p[k] - c[k]; }
+    const float d1 = dot3(ab, ap), d2 = dot3(ac, ap), d3 = dot3(ab, bp), d4 = dot3(ac, bp), d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    const float vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+    float u = 0.f, v = 0.f;                      // closest = a + u ab + v ac
+    if (d1 <= 0.f && d2 <= 0.f) { u = 0.f; v = 0.f; }
+    else if (d3 >= 0.f && d4 <= d3) { u = 1.f; v = 0.f; }
+    else if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { u = d1 / (d1 - d3); v = 0.f; }
+    else if (d6 >= 0.f && d5 <= d6) { u = 0.f; v = 1.f; }
+    else if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { u = 0.f; v = d2 / (d2 - d6); }
+    else if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) { v = (d4 - d3) / ((d4 - d3) + (d5 - d6)); u = 1.f - v; }
+    else { const float den = 1.0f / (va + vb + vc); u = vb * den; v = vc * den; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = a[k] + u * ab[k] + v * ac[k];
+}
+
+// squared distance (normalised units) from a point given in Q8 units (float) to a packed box: a lower bound of the
+// distance to anything inside the box (the boxes are quantised outwards)
+__device__ __forceinline__ float fbox_dist2(uint2 bx, const float* pq) {
+    float s = 0.f;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const float lo = (float)((bx.x >> (8 * ax)) & 255u), hi = (float)((bx.y >> (8 * ax)) & 255u);
+        const float d = fmaxf(fmaxf(lo - pq[ax], pq[ax] - hi), 0.f);
+        s += d * d;
+    }
+    return s * Q8_TO_D2;
+}
+
+__global__ void __launch_bounds__(SDF_THREADS, 4)
+k_sdf_exact(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SdfExactSmem& s = *reinterpret_cast<SdfExactSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool xform = (a.joints != nullptr);
+    int bucket_end[SDF_BUCKETS];
+    {
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < SDF_BUCKETS; ++k) { run += (int)w.counters[k]; bucket_end[k] = run; }
+    }
+    const int n_items = bucket_end[SDF_BUCKETS - 1];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s.item = (int)atomicAdd(&w.counters[SDF_BUCKETS], 1u); s.nact = 0; }
+        __syncthreads();
+        if (s.item >= n_items) break;
+        uint32_t code;
+        {
+            const int t = s.item;
+            int k = 0, start = 0;
+#pragma unroll
+            for (int q = 0; q + 1 < SDF_BUCKETS; ++q) if (t >= bucket_end[q]) { k = q + 1; start = bucket_end[q]; }
+            code = w.items[(size_t)k * 2 * B + (t - start)];
+        }
+        const int b = (int)(code >> 1), h = (int)(code & 1u), o = 1 - h;
+        const ushort4* cl_tri = h ? cl_l : cl_r;
+        const float* hd = w.hdr + (size_t)b * SDF_HDR;
+        float cen[3], tlo[3], thi[3];
+        const float scale = hd[16 * h + 3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { cen[c] = hd[16 * h + c]; tlo[c] = hd[16 * h + 4 + c]; thi[c] = hd[16 * h + 7 + c]; }
+        const float shx = hd[32], shy = hd[33], shz = hd[34], mask = hd[35];
+        auto load_vert = [&](int hand, int v, float* out) {
+            const float* p = a.verts + (((size_t)b * 2 + hand) * NV + v) * 3;
+            out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+            if (xform && hand == 1) { out[0] = -out[0] + shx; out[1] += shy; out[2] += shz; }
+        };
+        // ---- query vertices that can be inside at all: within the mesh's (y,z) extent and not right of its largest x
+        for (int v = tid; v < NV; v += SDF_THREADS) {
+            float p[3], pn[3];
+            load_vert(o, v, p);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) pn[c] = (p[c] - cen[c]) / scale;
+            s.outv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pn[0] <= thi[0] && pn[1] >= tlo[1] && pn[1] <= thi[1] && pn[2] >= tlo[2] && pn[2] <= thi[2])
+                s.act[atomicAdd(&s.nact, 1)] = make_float4(pn[0], pn[1], pn[2], __int_as_float(v));
+        }
+        __syncthreads();
+        const int nact = s.nact;
+        if (nact > 0) {
+            // ---- grid-hand geometry in normalised coordinates: vertices, Q8 face boxes, cluster boxes (as in k_sdf_dir)
+            for (int v = tid; v < NV; v += SDF_THREADS) {
+                float p[3];
+                load_vert(h, v, p);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) s.U[v * 3 + c] = (p[c] - cen[c]) / scale;
+            }
+            __syncthreads();
+            for (int c = warp; c < NCL; c += SDF_WARPS) {
+                const ushort4 id = cl_tri[c * 32 + lane];
+                int lo[3] = {255, 255, 255}, hi[3] = {0, 0, 0};
+                if (id.w) {
+                    const float* A_ = s.U + 3 * id.x; const float* B_ = s.U + 3 * id.y; const float* C_ = s.U + 3 * id.z;
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const float l = fminf(A_[ax], fminf(B_[ax], C_[ax])), hgh = fmaxf(A_[ax], fmaxf(B_[ax], C_[ax]));
+                        lo[ax] = max(0, min(255, (int)floorf((l + 1.0f) * 128.0f - 1e-3f)));
+                        hi[ax] = max(0, min(255, (int)ceilf((hgh + 1.0f) * 128.0f + 1e-3f)));
+                    }
+                }
+                const uint32_t far = 255u << 24;
+                s.fbox[c * 32 + lane] = id.w ? make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16),
+                                                          (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16))
+                                             : make_uint2(far, far);
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) { lo[ax] = __reduce_min_sync(0xffffffffu, lo[ax]); hi[ax] = __reduce_max_sync(0xffffffffu, hi[ax]); }
+                if (lane == 0)
+                    s.cl_box[c] = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 8) | ((uint32_t)lo[2] << 16),
+                                             (uint32_t)hi[0] | ((uint32_t)hi[1] << 8) | ((uint32_t)hi[2] << 16));
+            }
+            __syncthreads();
+            // ---- one warp per active vertex: inside test, then (inside only) the exact nearest face
+            for (int i = warp; i < nact; i += SDF_WARPS) {
+                const float4 av = s.act[i];
+                const float p[3] = {av.x, av.y, av.z};
+                const int v = __float_as_int(av.w);
+                const float pq[3] = {(p[0] + 1.0f) * 128.0f, (p[1] + 1.0f) * 128.0f, (p[2] + 1.0f) * 128.0f};     // Q8 units
+                // clusters / faces whose (y,z) box contains the ray and that reach beyond p in x (boxes are quantised
+                // outwards by at least 1e-3 Q8 units; 1e-2 more absorbs the rounding of pq)
+                auto ray_box = [&](uint2 bx) {
+                    return pq[1] >= (float)((bx.x >> 8) & 255u) - 1e-2f && pq[1] <= (float)((bx.y >> 8) & 255u) + 1e-2f &&
+                           pq[2] >= (float)((bx.x >> 16) & 255u) - 1e-2f && pq[2] <= (float)((bx.y >> 16) & 255u) + 1e-2f &&
+                           pq[0] <= (float)(bx.y & 255u) + 1e-2f && (bx.x >> 24) == 0u;
+                };
+                int crossings = 0;
+                uint32_t m0 = __ballot_sync(0xffffffffu, ray_box(s.cl_box[lane]));
+                uint32_t m1 = __ballot_sync(0xffffffffu, lane + 32 < NCL && ray_box(s.cl_box[min(lane + 32, NCL - 1)]));
+                for (int half = 0; half < 2; ++half) {
+                    for (uint32_t mm = half ? m1 : m0; mm; mm &= mm - 1u) {
+                        const int slot = (__ffs(mm) - 1 + 32 * half) * 32 + lane;
+                        if (ray_box(s.fbox[slot])) {
+                            const ushort4 id = cl_tri[slot];
+                            float x;
+                            if (ray_hit(s.U, id.x, id.y, id.z, p[1], p[2], x) && x > p[0]) ++crossings;
+                        }
+                    }
+                }
+                crossings = __reduce_add_sync(0xffffffffu, crossings);
+                if (!(crossings & 1)) continue;                    // warp-uniform: outside
+                // nearest face: clusters nearest box first, one face per lane, until no unvisited box can be closer
+                float lb[2];
+                lb[0] = fbox_dist2(s.cl_box[lane], pq);
+                lb[1] = (lane + 32 < NCL) ? fbox_dist2(s.cl_box[lane + 32], pq) : 3e30f;
+                float best = 3e30f;
+                int best_slot = 0;
+                for (int it = 0; it < NCL; ++it) {
+                    float mlb = fminf(lb[0], lb[1]);
+                    int which = (lb[0] <= lb[1]) ? lane : lane + 32;
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) {
+                        const float m2 = __shfl_xor_sync(0xffffffffu, mlb, sft);
+                        const int w2 = __shfl_xor_sync(0xffffffffu, which, sft);
+                        if (m2 < mlb || (m2 == mlb && w2 < which)) { mlb = m2; which = w2; }
+                    }
+                    if (mlb >= best) break;
+                    const int slot = which * 32 + lane;
+                    const uint2 fb = s.fbox[slot];
+                    float d2 = 3e30f;
+                    if ((fb.x >> 24) == 0u && fbox_dist2(fb, pq) < best) {
+                        const ushort4 id = cl_tri[slot];
+                        d2 = pt_tri_dist2(p, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z);
+                    }
+                    // warp argmin (ties: lowest slot), folded into the running best
+                    float dm = d2;
+                    int sm = slot;
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) {
+                        const float d3 = __shfl_xor_sync(0xffffffffu, dm, sft);
+                        const int s3 = __shfl_xor_sync(0xffffffffu, sm, sft);
+                        if (d3 < dm || (d3 == dm && s3 < sm)) { dm = d3; sm = s3; }
+                    }
+                    if (dm < best) { best = dm; best_slot = sm; }
+                    if (which == lane) lb[0] = 3e30f;
+                    if (which == lane + 32) lb[1] = 3e30f;
+                }
+                if (lane == 0) {
+                    const ushort4 id = cl_tri[best_slot];
+                    float cpt[3];
+                    pt_tri_closest(p, s.U + 3 * id.x, s.U + 3 * id.y, s.U + 3 * id.z, cpt);
+                    const float d[3] = {p[0] - cpt[0], p[1] - cpt[1], p[2] - cpt[2]};
+                    const float psi = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                    const float inv = psi > 0.f ? 1.0f / psi : 0.f;
+                    s.outv[v] = make_float4(psi, d[0] * inv, d[1] * inv, d[2] * inv);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- per-vertex outputs of the query hand o
+        const size_t ov0 = (size_t)b * (2 * NV) + o * NV;
+        const bool want_shift = a.gshift && o == 1;
+        const float kbase = mask * a.grad_scale * 0.25f / scale;       // d psi / d vertex = d psi / d p / scale ; loss = sum(psi) / 4
+        float sums[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int v = tid; v < NV; v += SDF_THREADS) {
+            const float4 r = s.outv[v];
+            sums[0] += r.x;
+            if (a.per_vert) a.per_vert[ov0 + v] = r.x;
+            if (a.origin) a.origin[ov0 + v] = r.x * scale;
+            float g[3] = {kbase * r.y, kbase * r.z, kbase * r.w};
+            sums[1] += g[0]; sums[2] += g[1]; sums[3] += g[2];
+            if (a.gverts) {
+                if (xform && o == 1) g[0] = -g[0];
+                float* gp = a.gverts + (ov0 + v) * 3;
+                gp[0] = g[0]; gp[1] = g[1]; gp[2] = g[2];
+            }
+        }
+        block_sum4(sums, want_shift ? 4 : 1, s.red);
+        if (tid == 0) w.parts[b * 2 + h] = sums[0];
+        if (want_shift && tid >= 1 && tid < 4) a.gshift[(size_t)b * 3 + (tid - 1)] = sums[tid];
+    }
+}
+
+int launch_sdf_exact(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
+    if (B <= 0) return IHMR_OK;
+    if (!a.ws) { set_error("sdf_exact: no workspace"); return IHMR_E_INVALID; }
+    static unsigned long long configured = 0ull;
+    static int ctas_per_sm = 0;
+    if (int rc = ensure_dynamic_smem(k_sdf_exact, sizeof(SdfExactSmem), configured)) return rc;
+    if (ctas_per_sm == 0) {
+        int n = 0;
+        IHMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sdf_exact, SDF_THREADS, sizeof(SdfExactSmem)));
+        if (n < 1) { set_error("sdf_exact: the kernel does not fit on an SM"); return IHMR_E_CUDA; }
+        ctas_per_sm = n;
+    }
+    const SdfWs w = sdf_ws_carve(a.ws, B);
+    IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, (SDF_BUCKETS + 1) * 4, st));
+    SdfArgs pa = a;
+    pa.gzero = nullptr;                 // (the skipped directions get explicit zeros in this mode)
+    k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, pa, w);
+    IHMR_LAUNCH_OK();
+    const int grid = std::min(std::min(m->num_sms * ctas_per_sm, SDF_MAX_GRID), 2 * B);
+    k_sdf_exact<<<grid, SDF_THREADS, sizeof(SdfExactSmem), st>>>(B, pa, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
+                                                               reinterpret_cast<const ushort4*>(m->cl_tri[1]));
+    IHMR_LAUNCH_OK();
+    if (a.losses) {
+        k_sdf_finish<<<(B + 255) / 256, 256, 0, st>>>(B, w.parts, a.hand_type, a.losses);
+        IHMR_LAUNCH_OK();
+    }
+    return IHMR_OK;
+}
+
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     if (B <= 0) return IHMR_OK;
     if (!a.ws) { set_error("sdf: no workspace"); return IHMR_E_INVALID; }

@@ -36,8 +36,12 @@ class _SdfFn(torch.autograd.Function):
         grad = torch.empty_like(hv) if need_grad else None
         rob = float(module.robustifier) if module.robustifier else 0.0
         ws = torch.empty(max(1, model._lib.ihmr_sdf_workspace_bytes(B)), device=dev, dtype=torch.uint8)
-        _lib.check(model._lib.ihmr_sdf_loss(model.handle, B, _ptr(hv), _ptr(losses), _ptr(per_vert), _ptr(origin),
-                                            _ptr(grad), rob, _ptr(ws), ws.numel(), _stream(dev)), "ihmr_sdf_loss")
+        if getattr(module, "exact", False):
+            _lib.check(model._lib.ihmr_sdf_loss_exact(model.handle, B, _ptr(hv), _ptr(losses), _ptr(per_vert), _ptr(origin),
+                                                      _ptr(grad), _ptr(ws), ws.numel(), _stream(dev)), "ihmr_sdf_loss_exact")
+        else:
+            _lib.check(model._lib.ihmr_sdf_loss(model.handle, B, _ptr(hv), _ptr(losses), _ptr(per_vert), _ptr(origin),
+                                                _ptr(grad), rob, _ptr(ws), ws.numel(), _stream(dev)), "ihmr_sdf_loss")
         ctx.grad = grad
         ctx.mark_non_differentiable(per_vert, origin)
         return losses, per_vert, origin
@@ -77,6 +81,19 @@ class SDFLoss(nn.Module):
         if return_origin_scale_loss:
             return losses, origin
         return losses
+
+
+class SDFLossExact(SDFLoss):
+    """NOT the reference's function — the exact, grid-free penetration mode of SURVEY.md §8(f) rank 3 behind the same
+    call signature: per vertex the exact distance to the other hand's mesh if the vertex is inside it, else 0 (the limit
+    of the 32^3 field for an infinitely fine grid; no 7 mm voxel quantisation).  Use it by name; ``SDFLoss`` stays the
+    reference-parity module."""
+    exact = True
+
+    def __init__(self, faces_right, faces_left, grid_size=32, robustifier=None, debugging=False):
+        if robustifier:
+            raise ValueError("the exact mode has no robustifier")
+        super().__init__(faces_right, faces_left, grid_size, None, debugging)
 
 
 class SDFLoss_Single(SDFLoss):

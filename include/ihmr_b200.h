@@ -106,6 +106,14 @@ int ihmr_sdf_loss(const ihmr_model_t* model, int n_frames, const float* hand_ver
                   float* per_vert, float* origin_scale, float* grad_hand_verts, float robustifier,
                   void* workspace, size_t workspace_bytes, ihmr_stream_t stream);
 
+/* EXACT (grid-free) penetration mode — NOT the reference's function, a separately named
+ * alternative: per query vertex the exact distance to the other hand's mesh if the vertex is inside it (odd +x ray
+ * crossing parity) else 0, in the same normalised units / metres, same loss = sum / 4, same outputs and gradient
+ * convention as ihmr_sdf_loss.  It is what the reference's 32^3 field converges to for an infinitely fine grid. */
+int ihmr_sdf_loss_exact(const ihmr_model_t* model, int n_frames, const float* hand_verts, float* losses,
+                        float* per_vert, float* origin_scale, float* grad_hand_verts, void* workspace,
+                        size_t workspace_bytes, ihmr_stream_t stream);
+
 /* Diagnostic variant for tools/tests: same kernels, additionally fills stats (n,32) int32 (zeroed
  * by the caller): per grid hand h in {0,1}: [2h] voxels evaluated, [2h+1] search rounds, [4+h] query
  * vertices inside the grid box, [16+h] direction finished by the prep kernel (boxes cannot meet);

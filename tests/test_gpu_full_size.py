@@ -186,3 +186,30 @@ def test_sdf_small_capacity_build_takes_every_overflow_path(model_root):
     out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_gpu_parity.py"),
                           "-k", "full_loop_vs_golden or value_and_grad"], env=env, cwd=root, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:]
+
+
+@pytest.mark.parametrize("mode,start,count", [("collision", 512, 10), ("typical", 0, 12)])
+def test_exact_penetration_mode_vs_bruteforce_oracle(layers, oracle_layers, mode, start, count):
+    """The separately named exact (grid-free) mode (not the reference's function) against its
+    brute-force CPU statement: same inside set, per-vertex distances, loss and gradient."""
+    from ihmr_b200 import sdf_loss
+    from oracle import sdf_exact_oracle as EO
+    hv_cpu = _two_hand_verts(oracle_layers, mode, start, count)
+    l_ref, pv_ref, o_ref, g_ref = EO.exact_penetration(hv_cpu.numpy(), oracle_layers[0].faces, oracle_layers[1].faces)
+    hv = hv_cpu.cuda().requires_grad_(True)
+    l, pv, o = sdf_loss.SDFLossExact(layers[0].faces, layers[1].faces).cuda()(hv, return_per_vert_loss=True, return_origin_scale_loss=True)
+    l.sum().backward()
+    pv, o, g = pv.detach().cpu().numpy(), o.cpu().numpy(), hv.grad.cpu().numpy()
+    assert np.array_equal(pv > 0, pv_ref > 0)                                   # the same vertices are inside
+    if mode == "collision":
+        assert (pv_ref > 0).sum() > 50 * count // 10
+    assert np.abs(pv - pv_ref).max() <= 2e-6 and np.abs(o - o_ref).max() <= 1e-6
+    assert np.abs(l.detach().cpu().numpy() - l_ref).max() <= 1e-5 * max(1.0, np.abs(l_ref).max())
+    # gradient: unit direction / (4 scale); ill-conditioned only where psi ~ 0
+    big = pv_ref.reshape(count, 2, 778) > 1e-3
+    assert np.abs(g - g_ref)[big].max() <= 2e-3 * np.abs(g_ref).max()
+    # and it is a different function from the grid mode (coarser there), of the same magnitude
+    lg = sdf_loss.SDFLoss(layers[0].faces, layers[1].faces).cuda()(hv_cpu.cuda())
+    if mode == "collision":
+        ratio = float(l.detach().sum() / lg.sum())
+        assert 0.5 < ratio < 2.0 and not torch.allclose(l.detach(), lg)

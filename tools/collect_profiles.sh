@@ -13,6 +13,7 @@ if [ $WHAT = all ] || [ $WHAT = kernels ]; then
   # 2) every kernel of one warm + one steady iteration per stage: throughput, memory, scheduler, occupancy sections
   timeout 1200 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section SchedulerStats --section WarpStateStats \
       --section Occupancy --section LaunchStats --section InstructionStats --section ComputeWorkloadAnalysis \
+      --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_tensor.sum \
       --clock-control none -k regex:^k_ -o /tmp/ncu/${TAG}_kernels -f python tools/prof_stage_iters.py > gpurun_out/${TAG}_kernels.log 2>&1
   ncu -i /tmp/ncu/${TAG}_kernels.ncu-rep --page raw --csv > gpurun_out/${TAG}_kernels_raw.csv 2>/dev/null
 fi
