@@ -37,6 +37,14 @@ constexpr int G = 32;
 #ifndef SDF_NTHREADS
 #define SDF_NTHREADS 256
 #endif
+#ifndef SDF_ROLL
+#define SDF_ROLL 1                  // 1: the per-thread vertex loops stay rolled (code size: the kernel is instruction-fetch sensitive)
+#endif
+#if SDF_ROLL
+#define SDF_SLOT_LOOP _Pragma("unroll 1")
+#else
+#define SDF_SLOT_LOOP _Pragma("unroll")
+#endif
 constexpr int SDF_THREADS = SDF_NTHREADS;
 constexpr int SDF_WARPS = SDF_THREADS / 32;
 constexpr int SDF_CPT = G * G / SDF_THREADS;   // (z,y) columns per thread in the scans
@@ -272,6 +280,22 @@ __device__ __forceinline__ void pair_test(SdfSmem& s, const ushort4* __restrict_
     if (bits < atomicMin(&s.best[vi], bits)) atomicExch(&s.hintw[vi], (uint32_t)slot);
 }
 
+// the same test out of line: the queue-full paths are rare and must not be inlined at every reservation site
+__device__ __noinline__ void pair_test_slow(SdfSmem& s, const ushort4* __restrict__ cl_tri, int vi, int slot) { pair_test(s, cl_tri, vi, slot); }
+
+// one (face, column) item of the parity rasterisation: the exact ray test; a hit toggles the bits of all voxels whose
+// centre lies strictly left of the crossing
+__device__ __forceinline__ void ray_item(SdfSmem& s, const ushort4* __restrict__ cl_tri, int slot, int col) {
+    const ushort4 id = cl_tri[slot];
+    float x;
+    if (!ray_hit(s.U, id.x, id.y, id.z, voxel_center(col & 31), voxel_center(col >> 5), x)) return;
+    int cnt = min(G, max(0, (int)ceilf((x * G + (G - 1)) * 0.5f)));
+    while (cnt < G && x > voxel_center(cnt)) ++cnt;
+    while (cnt > 0 && !(x > voxel_center(cnt - 1))) --cnt;
+    if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+}
+__device__ __noinline__ void ray_item_slow(SdfSmem& s, const ushort4* __restrict__ cl_tri, int slot, int col) { ray_item(s, cl_tri, slot, col); }
+
 // packed Q8 voxel centre -> index into the hint table: the low bits of (x, y, z), so that a block of
 // 8 x 16 x 16 neighbouring voxels never collides
 __device__ __forceinline__ int hint_index(uint32_t q8) {
@@ -421,7 +445,7 @@ __global__ void k_sdf_finish(int B, const float* __restrict__ parts, const float
 }
 
 #define SDF_STAT(i)                                                                       \
-    if (a.stats && tid == 0) {                                                            \
+    if (kStats && tid == 0) {                                                            \
         const long long t_now = clock64();                                                \
         atomicAdd(&a.stats[b * 32 + 18 + (i)], (int)(t_now - t_prev));                    \
         t_prev = t_now;                                                                   \
@@ -433,7 +457,8 @@ __global__ void k_sdf_finish(int B, const float* __restrict__ parts, const float
 // parity, scan, worklist, seeds + candidates, exact tests, finish, sample + outputs)
 
 // kStatic = false compiles the static-grid cache out (stages in which both hands move)
-template <bool kStatic>
+// kStats = true only for ihmr_sdf_stats (tools, capacity tests): the counters cost ~300 instructions of code
+template <bool kStatic, bool kStats>
 __global__ void __launch_bounds__(SDF_THREADS, SDF_MIN_CTAS)
 k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ushort4* __restrict__ cl_l) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -522,6 +547,10 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
         int nact = 0;
         {
             int reg[4] = {G, -1, G, -1};         // this thread's marked columns: y min, y max, z min, z max
+#if SDF_ROLL
+            float nx[3] = {3e30f, 0.f, 0.f};     // the next vertex is in flight while this one is processed
+            if (tid < NV) load_vert(o, tid, nx);
+#else
             float pq[SDF_SLOTS][3];              // all loads in flight before the first use
 #pragma unroll
             for (int sl = 0; sl < SDF_SLOTS; ++sl) {
@@ -529,11 +558,19 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                 pq[sl][0] = 3e30f; pq[sl][1] = 0.f; pq[sl][2] = 0.f;         // beyond whi[0]: rejected
                 if (v < NV) load_vert(o, v, pq[sl]);
             }
-#pragma unroll
+#endif
+            SDF_SLOT_LOOP
             for (int sl = 0; sl < SDF_SLOTS; ++sl) {
                 float fr[3];
                 int i0[3];
+#if SDF_ROLL
+                const float cur[3] = {nx[0], nx[1], nx[2]};
+                nx[0] = 3e30f;                                                // beyond whi[0]: rejected
+                if (tid + (sl + 1) * SDF_THREADS < NV) load_vert(o, tid + (sl + 1) * SDF_THREADS, nx);
+                if (!locate(cur, fr, i0)) continue;
+#else
                 if (!locate(pq[sl], fr, i0)) continue;
+#endif
                 ++nact;
                 // A voxel can only be inside (odd +x crossings) if its (y,z) lies within the
                 // mesh's (y,z) extent and its x is left of the mesh's largest x: other corners
@@ -565,7 +602,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             }
         }
         const bool any_block = __syncthreads_or(any);
-        if (a.stats) {
+        if (kStats) {
             const int n = __reduce_add_sync(0xffffffffu, nact);
             if (lane == 0) atomicAdd(&a.stats[b * 32 + 4 + h], n);
         }
@@ -638,16 +675,6 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             // ---- parity of the marked columns, two steps so that the ray tests run with full warps:
             //      (1) thread per face: lattice points inside its (y,z) box whose column is marked
             //          -> (face, column) items; (2) thread per item: the exact ray test
-            auto ray_item = [&](int slot, int col) {
-                const ushort4 id = cl_tri[slot];
-                float x;
-                if (!ray_hit(s.U, id.x, id.y, id.z, voxel_center(col & 31), voxel_center(col >> 5), x)) return;
-                // voxels whose centre lies strictly left of the crossing
-                int cnt = min(G, max(0, (int)ceilf((x * G + (G - 1)) * 0.5f)));
-                while (cnt < G && x > voxel_center(cnt)) ++cnt;
-                while (cnt > 0 && !(x > voxel_center(cnt - 1))) --cnt;
-                if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
-            };
             const int ry0 = s.region[0], ry1 = s.region[1], rz0 = s.region[2], rz1 = s.region[3];
             uint32_t* rqueue = s.queue + warp * QSEG;
             int rq = 0;                                          // fill of this warp's segment (warp-uniform)
@@ -673,21 +700,19 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                         const int pos = rq + __popc(m & lt_mask);
                         if (pos < QSEG) rqueue[pos] = ((uint32_t)face << 10) | (uint32_t)col;
                         else {
-                            ray_item(face, col);
-                            if (a.stats) atomicAdd(&a.stats[b * 32 + 11], 1);
+                            ray_item_slow(s, cl_tri, face, col);
+                            if (kStats) atomicAdd(&a.stats[b * 32 + 11], 1);
                         }
                     }
                     rq += __popc(m);
                 };
                 const bool cover = (j1 >= j0) && (k1 >= k0);
                 const bool small = cover && (j1 - j0 <= 1) && (k1 - k0 <= 1);
-#pragma unroll
-                for (int dk = 0; dk < 2; ++dk)
-#pragma unroll
-                    for (int dj = 0; dj < 2; ++dj) {
-                        const int k = k0 + dk, j = j0 + dj, col = k * G + j;
-                        push(small && k <= k1 && j <= j1 && (stat ? s.coloff[col & (G * G - 1)] != 0 : s.needed[col & (G * G - 1)] != 0u), slot, col);
-                    }
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {          // (rolled: one reservation site)
+                    const int k = k0 + (i >> 1), j = j0 + (i & 1), col = k * G + j;
+                    push(small && k <= k1 && j <= j1 && (stat ? s.coloff[col & (G * G - 1)] != 0 : s.needed[col & (G * G - 1)] != 0u), slot, col);
+                }
                 uint32_t bigm = __ballot_sync(0xffffffffu, cover && !small);
                 while (bigm) {
                     const int src = __ffs(bigm) - 1;
@@ -696,16 +721,19 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                     const int fk0 = __shfl_sync(0xffffffffu, k0, src), fk1 = __shfl_sync(0xffffffffu, k1, src);
                     const int ff = c * 32 + src;
                     const int nj = fj1 - fj0 + 1, npts = nj * (fk1 - fk0 + 1);
+                    // t / nj for t < 1024, nj <= 32 in floating point: (t + 0.5) / nj stays 1/64 away from every integer
+                    const float rnj = __fdividef(1.0f, (float)nj);
+#pragma unroll 1
                     for (int t0 = 0; t0 < npts; t0 += 32) {
-                        const int t = t0 + lane, dk = t / nj, col = (fk0 + dk) * G + fj0 + (t - dk * nj);
+                        const int t = t0 + lane, dk = (int)(((float)t + 0.5f) * rnj), col = (fk0 + dk) * G + fj0 + (t - dk * nj);
                         push(t < npts && (stat ? s.coloff[col & (G * G - 1)] != 0 : s.needed[col & (G * G - 1)] != 0u), ff, col);
                     }
                 }
             }
             if (lane == 0) s.qcnt[warp] = min(rq, QSEG);
-            if (a.stats && lane == 0) atomicAdd(&a.stats[b * 32 + 9], rq);
+            if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 9], rq);
             __syncthreads();
-            for_each_queued([&](uint32_t e) { ray_item((int)(e >> 10), (int)(e & 1023u)); });
+            for_each_queued([&](uint32_t e) { ray_item(s, cl_tri, (int)(e >> 10), (int)(e & 1023u)); });
             __syncthreads();
             if (stat) {                  // the new columns' parity words are known from now on
                 for (int c = tid; c < G * G; c += SDF_THREADS)
@@ -723,7 +751,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                 s.work[c] = wk;
                 cnt[i] = __popc(wk);
             }
-            if (a.stats) {
+            if (kStats) {
                 int nm = 0;
                 for (int i = 0; i < SDF_CPT; ++i) nm += __popc(s.needed[tid * SDF_CPT + i]);
                 nm = __reduce_add_sync(0xffffffffu, nm);
@@ -773,7 +801,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                 any_todo = __syncthreads_or(mytodo);
                 if (any_todo && !geom_ready) geometry();
             }
-            if (a.stats) {
+            if (kStats) {
                 nhit = __reduce_add_sync(0xffffffffu, nhit);
                 if (lane == 0 && nhit) atomicAdd(&a.stats[b * 32 + 13], nhit);
                 if (tid == 0) { atomicAdd(&a.stats[b * 32 + 2 * h], nvox); atomicAdd(&a.stats[b * 32 + 10], 1); }
@@ -847,7 +875,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                         const int seed = __shfl_sync(0xffffffffu, myseed, k);
                         const uint32_t m0 = __ballot_sync(0xffffffffu, qbox_4d2(s.cl_box[lane], q) < thr);
                         const uint32_t m1 = __ballot_sync(0xffffffffu, lane + 32 < NCL && qbox_4d2(s.cl_box[min(lane + 32, NCL - 1)], q) < thr);
-                        if (a.stats && lane == 0) atomicAdd(&a.stats[b * 32 + 6], __popc(m0) + __popc(m1));
+                        if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 6], __popc(m0) + __popc(m1));
                         const uint32_t ventry = ((uint32_t)v << 16) | (uint32_t)lane;
                         auto cluster = [&](int c) {
                             const int slot = c * 32 + lane;
@@ -859,8 +887,8 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                                 if (ok) wqueue[wq + __popc(okm & lt_mask)] = ventry + ((uint32_t)c << 5);
                                 wq += n;
                             } else if (ok) {
-                                pair_test(s, cl_tri, v, slot);          // does not fit the segment: test in place
-                                if (a.stats) atomicAdd(&a.stats[b * 32 + 12], 1);
+                                pair_test_slow(s, cl_tri, v, slot);     // does not fit the segment: test in place
+                                if (kStats) atomicAdd(&a.stats[b * 32 + 12], 1);
                             }
                             ncand += n;
                         };
@@ -869,10 +897,10 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                     }
                 }
                 if (lane == 0) s.qcnt[warp] = wq;
-                if (a.stats && lane == 0) atomicAdd(&a.stats[b * 32 + 7], ncand);
+                if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 7], ncand);
                 __syncthreads();
                 SDF_STAT(6)
-                if (a.stats && tid == 0) atomicAdd(&a.stats[b * 32 + 2 * h + 1], 1);
+                if (kStats && tid == 0) atomicAdd(&a.stats[b * 32 + 2 * h + 1], 1);
                 for_each_queued([&](uint32_t e) { pair_test(s, cl_tri, (int)(e >> 16), (int)(e & 0xffffu)); });
                 __syncthreads();
                 SDF_STAT(7)
@@ -916,7 +944,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
         // d psi / d vertex = (G/2) * d psi / d(ix) / scale ; loss = sum(rho) / 4
         const float kbase = mask * a.grad_scale * 0.25f * (0.5f * G) / scale;
         float sums[4] = {0.f, 0.f, 0.f, 0.f};      // sum of rho, gradient sum xyz
-#pragma unroll
+        SDF_SLOT_LOOP
         for (int sl = 0; sl < SDF_SLOTS; ++sl) {
             const int v = tid + sl * SDF_THREADS;
             if (v >= NV) continue;
@@ -1240,22 +1268,23 @@ int launch_sdf_exact(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t 
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     if (B <= 0) return IHMR_OK;
     if (!a.ws) { set_error("sdf: no workspace"); return IHMR_E_INVALID; }
-    static unsigned long long configured[2] = {0ull, 0ull};
-    static int ctas_per_sm[2] = {0, 0};
+    static unsigned long long configured[3] = {0ull, 0ull, 0ull};
+    static int ctas_per_sm[3] = {0, 0, 0};
     const bool use_static = a.static_grid_mask && a.pcache && a.phic && a.hints;
-    auto kernel = use_static ? k_sdf_dir<true> : k_sdf_dir<false>;
-    if (int rc = ensure_dynamic_smem(kernel, sizeof(SdfSmem), configured[use_static])) return rc;
-    if (ctas_per_sm[use_static] == 0) {
+    const int kv = a.stats ? 2 : (use_static ? 1 : 0);
+    auto kernel = a.stats ? k_sdf_dir<false, true> : (use_static ? k_sdf_dir<true, false> : k_sdf_dir<false, false>);
+    if (int rc = ensure_dynamic_smem(kernel, sizeof(SdfSmem), configured[kv])) return rc;
+    if (ctas_per_sm[kv] == 0) {
         int n = 0;
         IHMR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, SDF_THREADS, sizeof(SdfSmem)));
         if (n < 1) { set_error("sdf: the kernel does not fit on an SM"); return IHMR_E_CUDA; }
-        ctas_per_sm[use_static] = n;
+        ctas_per_sm[kv] = n;
     }
     const SdfWs w = sdf_ws_carve(a.ws, B);
     IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, (SDF_BUCKETS + 1) * 4, st));
     k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, a, w);
     IHMR_LAUNCH_OK();
-    const int grid = std::min(std::min(m->num_sms * ctas_per_sm[use_static], SDF_MAX_GRID), 2 * B);
+    const int grid = std::min(std::min(m->num_sms * ctas_per_sm[kv], SDF_MAX_GRID), 2 * B);
     kernel<<<grid, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
                                                        reinterpret_cast<const ushort4*>(m->cl_tri[1]));
     IHMR_LAUNCH_OK();
