@@ -15,9 +15,10 @@
 //        (y,z) lattice point is tested against that +x ray; a hit toggles the bits of all
 //        voxels left of the crossing                                                   (A4)
 //     4. phi = min point-triangle distance for every voxel that is both marked and inside.
-//        Per voxel (one warp each, no block barrier): nearest cluster box -> nearest face box
-//        in it -> one exact test = a tight upper bound; then only the faces whose box is
-//        closer than that bound are queued, and the exact tests run densely, one per thread.
+//        A seed face per voxel (the nearest face of the previous iteration, else nearest
+//        cluster box -> nearest face box) and its exact distance, one voxel per thread = a
+//        tight upper bound; then, one warp per voxel, only the faces whose box is closer than
+//        that bound are queued, and the exact tests run densely, one per thread.
 //     5. trilinear sampling with grid_sample(align_corners=False, zeros) semantics, its
 //        gradient w.r.t. the query vertex, per-direction loss part                (A3, A5, A6)
 //
@@ -65,16 +66,14 @@ constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
 #ifndef SDF_V_CHUNK
 #define SDF_V_CHUNK 128             // voxels per search round
 #endif
-#ifndef SDF_TV
-#define SDF_TV 8                    // voxels a warp takes at a time (the seeds are tested one per lane)
-#endif
-constexpr int PHI_CAP = SDF_PHI_CAP, Q_CAP = SDF_Q_CAP, V_CHUNK = SDF_V_CHUNK, TV = SDF_TV;
+constexpr int PHI_CAP = SDF_PHI_CAP, Q_CAP = SDF_Q_CAP, V_CHUNK = SDF_V_CHUNK;
 constexpr int QSEG = Q_CAP / SDF_WARPS;   // candidate queue segment of one warp
-static_assert(PHI_CAP <= 65536 && TV <= 32 && V_CHUNK >= TV, "queue entries pack the voxel index into 16 bits");
+static_assert(PHI_CAP <= 65536 && V_CHUNK >= 1, "queue entries pack the voxel index into 16 bits");
 constexpr int SDF_SPILL = NV * 8;   // a direction evaluates at most 8 voxels per query vertex
 constexpr int SDF_MAX_GRID = 160 * 8;
 constexpr int SDF_HINTS = 2048;     // nearest-face hints per (frame, direction): one u16 per voxel of an 8 x 16 x 16 block (wraps)
 constexpr uint32_t HINT_DONE = 0xffffffffu, HINT_NONE = 0xfffffffeu;   // states of a voxel in hintw (else: seed slot)
+constexpr uint32_t SEED_NEW = 0x40000000u;                             // | seed slot: found in this call, distance not measured yet
 constexpr int SDF_PCACHE = G * G + G;   // words per frame of the static-grid parity cache: 1024 columns + 32 words of "known" bits
 constexpr int SDF_HDR = 40;         // floats per frame header (see k_sdf_prep)
 constexpr float Q8_TO_D2 = 1.0f / 16384.0f;         // Q8 units squared -> normalised units squared
@@ -780,64 +779,47 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                 }
             }
             __syncthreads();
-            // ---- static grid: what is known about each voxel from the previous iterations — its finished distance, or
-            //      at least its nearest face (a seed)
+            // ---- what is known about each voxel from the previous iteration (thread per voxel): the face that was nearest
+            //      (a seed: its exact distance is an upper bound of the minimum), or — static grid — the finished distance
             bool any_todo = true;
             int nhit = 0;
-            if (stat) {
-                bool mytodo = false;
+            {
+                bool mytodo = false, myblank = false;
                 for (int i = tid; i < nvox; i += SDF_THREADS) {
                     uint32_t state = HINT_NONE;
                     const uint32_t q = s.worklist[i];
-                    const int hi_ = hint_index(q);
-                    const uint32_t e = hint[hi_];
-                    if (((e >> 11) & 15u) == hint_tag(q) && (e & 2047u)) {
-                        if (e & 0x8000u) { state = HINT_DONE; s.best[i] = __float_as_uint(phic[hi_]); ++nhit; }
-                        else state = (e & 2047u) - 1u;
-                    }
-                    s.hintw[i] = state;
-                    mytodo = mytodo || state != HINT_DONE;
-                }
-                any_todo = __syncthreads_or(mytodo);
-                if (any_todo && !geom_ready) geometry();
-            }
-            if (kStats) {
-                nhit = __reduce_add_sync(0xffffffffu, nhit);
-                if (lane == 0 && nhit) atomicAdd(&a.stats[b * 32 + 13], nhit);
-                if (tid == 0) { atomicAdd(&a.stats[b * 32 + 2 * h], nvox); atomicAdd(&a.stats[b * 32 + 10], 1); }
-            }
-            SDF_STAT(5)
-            // ---- nearest face of every voxel.  Rounds of V_CHUNK voxels:
-            //   (S) warp per voxel, TV voxels at a time: distances to the NCL cluster boxes -> nearest cluster ->
-            //       distances to its <= 32 face boxes -> the face with the nearest box is the voxel's seed; the
-            //       seeds of the TV voxels are tested exactly, one per lane: best = an upper bound of the minimum
-            //   (B) warp per voxel: clusters whose box is closer than best (the cluster box is the union of the
-            //       face boxes, so it is never farther than any of them) -> their faces whose box is closer than
-            //       best -> (voxel, face) candidates.  A face that fails either test cannot be nearer than best.
-            //   (C) thread per candidate: exact point-triangle test, atomicMin into the voxel
-            for (int v0 = 0; v0 < nvox && any_todo; v0 += V_CHUNK) {
-                const int v1 = min(nvox, v0 + V_CHUNK);
-                uint32_t* wqueue = s.queue + warp * QSEG;      // candidates of this warp's voxels: no atomics
-                int wq = 0, ncand = 0;                           // fill (warp-uniform), candidates found
-                for (int t0 = v0 + warp * TV; t0 < v1; t0 += SDF_WARPS * TV) {
-                    const int nt = min(TV, v1 - t0);
-                    int myseed = -1;
-                    bool mydone = false;
-                    if (lane < nt) {
-                        if (stat) {
-                            const uint32_t st_ = s.hintw[t0 + lane];
-                            mydone = st_ == HINT_DONE;
-                            if (st_ < HINT_NONE) myseed = (int)st_;
-                        } else if (hint) {       // seeds carried over from the previous iteration of the refinement loop
-                            const uint32_t q = s.worklist[t0 + lane], e = hint[hint_index(q)];
-                            if (((e >> 11) & 15u) == hint_tag(q)) myseed = (int)(e & 2047u) - 1;
+                    if (hint) {
+                        const int hi_ = hint_index(q);
+                        const uint32_t e = hint[hi_];
+                        if (((e >> 11) & 15u) == hint_tag(q) && (e & 2047u)) {
+                            if (stat && (e & 0x8000u)) { state = HINT_DONE; s.best[i] = __float_as_uint(phic[hi_]); ++nhit; }
+                            else state = (e & 2047u) - 1u;
                         }
                     }
-                    const uint32_t have = __ballot_sync(0xffffffffu, myseed >= 0 || mydone);       // no seed search needed
-                    const uint32_t todo = __ballot_sync(0xffffffffu, lane < nt && !mydone);
-                    for (int k = 0; k < nt; ++k) {
-                        if ((have >> k) & 1u) continue;
-                        const uint32_t q = s.worklist[t0 + k];
+                    if (state < HINT_NONE && geom_ready) s.best[i] = __float_as_uint(voxel_face_dist2(s, cl_tri, q, (int)state));
+                    s.hintw[i] = state;
+                    mytodo = mytodo || state != HINT_DONE;
+                    myblank = myblank || state == HINT_NONE;
+                }
+                // (without a static grid the geometry is always there and every voxel is to do)
+                if (stat) {
+                    any_todo = __syncthreads_or(mytodo);
+                    if (any_todo && !geom_ready) {
+                        // (the seeds above had no geometry to be measured against yet)
+                        geometry();
+                        for (int i = tid; i < nvox; i += SDF_THREADS) {
+                            const uint32_t st_ = s.hintw[i];
+                            if (st_ < HINT_NONE) s.best[i] = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[i], (int)st_));
+                        }
+                    }
+                }
+                // ---- voxels without a seed (first iteration, stateless calls, newly touched voxels).
+                //   (S) warp per voxel: distances to the NCL cluster boxes -> nearest clusters -> their face boxes -> seed
+                //   then thread per voxel: the seed's exact distance
+                if (__syncthreads_or(myblank)) {
+                    for (int v = warp; v < nvox; v += SDF_WARPS) {
+                        if (s.hintw[v] != HINT_NONE) continue;
+                        const uint32_t q = s.worklist[v];
                         const uint32_t d0 = qbox_4d2(s.cl_box[lane], q);
                         const uint32_t d1 = (lane + 32 < NCL) ? qbox_4d2(s.cl_box[lane + 32], q) : 0xffffffffu;
                         const uint32_t dmin = __reduce_min_sync(0xffffffffu, min(d0, d1));
@@ -858,43 +840,64 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                             kf = min(kf, (fb.x >> 24) ? 0xffffffffu : kk);          // empty table slots never win
                         }
                         kf = __reduce_min_sync(0xffffffffu, kf);
-                        if (lane == k) myseed = (int)(kf & 2047u);
+                        __syncwarp();
+                        if (lane == 0) s.hintw[v] = SEED_NEW | (kf & 2047u);
                     }
-                    if (lane < nt && !mydone) {
-                        s.best[t0 + lane] = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[t0 + lane], myseed));
-                        s.hintw[t0 + lane] = (uint32_t)myseed;
+                    __syncthreads();
+                    for (int i = tid; i < nvox; i += SDF_THREADS) {
+                        const uint32_t st_ = s.hintw[i];
+                        if ((st_ & 0xc0000000u) == SEED_NEW) {
+                            const uint32_t slot = st_ & 2047u;
+                            s.best[i] = __float_as_uint(voxel_face_dist2(s, cl_tri, s.worklist[i], (int)slot));
+                            s.hintw[i] = slot;
+                        }
                     }
-                    __syncwarp();
-                    for (int k = 0; k < nt; ++k) {
-                        if (!((todo >> k) & 1u)) continue;
-                        const int v = t0 + k;
-                        const uint32_t q = s.worklist[v];
-                        const float bv = __uint_as_float(s.best[v]);
-                        // integer threshold: (float)d * Q4D2_TO_D2 < bv  <=>  d < bv / Q4D2_TO_D2 (a power of two: exact)
-                        const uint32_t thr = (uint32_t)fminf(ceilf(bv * (1.0f / Q4D2_TO_D2)), 4.0e9f);
-                        const int seed = __shfl_sync(0xffffffffu, myseed, k);
-                        const uint32_t m0 = __ballot_sync(0xffffffffu, qbox_4d2(s.cl_box[lane], q) < thr);
-                        const uint32_t m1 = __ballot_sync(0xffffffffu, lane + 32 < NCL && qbox_4d2(s.cl_box[min(lane + 32, NCL - 1)], q) < thr);
-                        if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 6], __popc(m0) + __popc(m1));
-                        const uint32_t ventry = ((uint32_t)v << 16) | (uint32_t)lane;
-                        auto cluster = [&](int c) {
-                            const int slot = c * 32 + lane;
-                            const uint2 fb = s.fbox[slot];
-                            const bool ok = qbox_4d2(fb, q) < thr && slot != seed && fb.x < (1u << 24);      // (not an empty table slot)
-                            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
-                            const int n = __popc(okm);
-                            if (wq + n <= QSEG) {                 // warp-uniform
-                                if (ok) wqueue[wq + __popc(okm & lt_mask)] = ventry + ((uint32_t)c << 5);
-                                wq += n;
-                            } else if (ok) {
-                                pair_test_slow(s, cl_tri, v, slot);     // does not fit the segment: test in place
-                                if (kStats) atomicAdd(&a.stats[b * 32 + 12], 1);
-                            }
-                            ncand += n;
-                        };
-                        for (uint32_t mm = m0; mm; mm &= mm - 1u) cluster(__ffs(mm) - 1);
-                        for (uint32_t mm = m1; mm; mm &= mm - 1u) cluster(__ffs(mm) + 31);
-                    }
+                    __syncthreads();
+                }
+            }
+            if (kStats) {
+                nhit = __reduce_add_sync(0xffffffffu, nhit);
+                if (lane == 0 && nhit) atomicAdd(&a.stats[b * 32 + 13], nhit);
+                if (tid == 0) { atomicAdd(&a.stats[b * 32 + 2 * h], nvox); atomicAdd(&a.stats[b * 32 + 10], 1); }
+            }
+            SDF_STAT(5)
+            // ---- nearest face of every voxel.  Rounds of V_CHUNK voxels:
+            //   (B) warp per voxel: clusters whose box is closer than best (the cluster box is the union of the
+            //       face boxes, so it is never farther than any of them) -> their faces whose box is closer than
+            //       best -> (voxel, face) candidates.  A face that fails either test cannot be nearer than best.
+            //   (C) thread per candidate: exact point-triangle test, atomicMin into the voxel
+            for (int v0 = 0; v0 < nvox && any_todo; v0 += V_CHUNK) {
+                const int v1 = min(nvox, v0 + V_CHUNK);
+                uint32_t* wqueue = s.queue + warp * QSEG;      // candidates of this warp's voxels: no atomics
+                int wq = 0, ncand = 0;                           // fill (warp-uniform), candidates found
+                for (int v = v0 + warp; v < v1; v += SDF_WARPS) {
+                    const int seed = (int)s.hintw[v];
+                    if (stat && seed == (int)HINT_DONE) continue;
+                    const uint32_t q = s.worklist[v];
+                    const float bv = __uint_as_float(s.best[v]);
+                    // integer threshold: (float)d * Q4D2_TO_D2 < bv  <=>  d < bv / Q4D2_TO_D2 (a power of two: exact)
+                    const uint32_t thr = (uint32_t)fminf(ceilf(bv * (1.0f / Q4D2_TO_D2)), 4.0e9f);
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, qbox_4d2(s.cl_box[lane], q) < thr);
+                    const uint32_t m1 = __ballot_sync(0xffffffffu, lane + 32 < NCL && qbox_4d2(s.cl_box[min(lane + 32, NCL - 1)], q) < thr);
+                    if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 6], __popc(m0) + __popc(m1));
+                    const uint32_t ventry = ((uint32_t)v << 16) | (uint32_t)lane;
+                    auto cluster = [&](int c) {
+                        const int slot = c * 32 + lane;
+                        const uint2 fb = s.fbox[slot];
+                        const bool ok = qbox_4d2(fb, q) < thr && slot != seed && fb.x < (1u << 24);      // (not an empty table slot)
+                        const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+                        const int n = __popc(okm);
+                        if (wq + n <= QSEG) {                 // warp-uniform
+                            if (ok) wqueue[wq + __popc(okm & lt_mask)] = ventry + ((uint32_t)c << 5);
+                            wq += n;
+                        } else if (ok) {
+                            pair_test_slow(s, cl_tri, v, slot);     // does not fit the segment: test in place
+                            if (kStats) atomicAdd(&a.stats[b * 32 + 12], 1);
+                        }
+                        ncand += n;
+                    };
+                    for (uint32_t mm = m0; mm; mm &= mm - 1u) cluster(__ffs(mm) - 1);
+                    for (uint32_t mm = m1; mm; mm &= mm - 1u) cluster(__ffs(mm) + 31);
                 }
                 if (lane == 0) s.qcnt[warp] = wq;
                 if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 7], ncand);

@@ -23,6 +23,7 @@ if [ $WHAT = all ] || [ $WHAT = sdf ]; then
       python tools/prof_stage_iters.py --stages 0,1,2 > gpurun_out/${TAG}_sdf.log 2>&1
   ncu -i /tmp/ncu/${TAG}_sdf.ncu-rep --page raw --csv > gpurun_out/${TAG}_sdf_raw.csv 2>/dev/null
   ncu -i /tmp/ncu/${TAG}_sdf.ncu-rep --page source --csv > gpurun_out/${TAG}_sdf_sass.csv 2>/dev/null
+  ncu -i /tmp/ncu/${TAG}_sdf.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/${TAG}_sdf_src.csv 2>/dev/null
   ncu -i /tmp/ncu/${TAG}_sdf.ncu-rep --page details > gpurun_out/${TAG}_sdf_details.txt 2>/dev/null
 fi
 ls -la gpurun_out | tail -12
