@@ -865,7 +865,8 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             //   (B) warp per voxel: clusters whose box is closer than best (the cluster box is the union of the
             //       face boxes, so it is never farther than any of them) -> their faces whose box is closer than
             //       best -> (voxel, face) candidates.  A face that fails either test cannot be nearer than best.
-            //   (C) thread per candidate: exact point-triangle test, atomicMin into the voxel
+            //   (C) the same warp, lane per candidate of its own queue segment: exact point-triangle test, atomicMin into
+            //       the voxel.  No block barrier between the rounds.
             for (int v0 = 0; v0 < nvox && any_todo; v0 += V_CHUNK) {
                 const int v1 = min(nvox, v0 + V_CHUNK);
                 uint32_t* wqueue = s.queue + warp * QSEG;      // candidates of this warp's voxels: no atomics
@@ -899,15 +900,18 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                     for (uint32_t mm = m0; mm; mm &= mm - 1u) cluster(__ffs(mm) - 1);
                     for (uint32_t mm = m1; mm; mm &= mm - 1u) cluster(__ffs(mm) + 31);
                 }
-                if (lane == 0) s.qcnt[warp] = wq;
+                // (C) by the same warp on its own segment: no block barrier between the rounds
+                __syncwarp();
+                for (int p2 = lane; p2 < wq; p2 += 32) {
+                    const uint32_t e = wqueue[p2];
+                    pair_test(s, cl_tri, (int)(e >> 16), (int)(e & 0xffffu));
+                }
+                __syncwarp();
                 if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 7], ncand);
-                __syncthreads();
-                SDF_STAT(6)
                 if (kStats && tid == 0) atomicAdd(&a.stats[b * 32 + 2 * h + 1], 1);
-                for_each_queued([&](uint32_t e) { pair_test(s, cl_tri, (int)(e >> 16), (int)(e & 0xffffu)); });
-                __syncthreads();
-                SDF_STAT(7)
             }
+            __syncthreads();
+            SDF_STAT(7)
             // ---- phi = distance
             for (int i = tid; i < nvox; i += SDF_THREADS) {
                 float d = __uint_as_float(s.best[i]);

@@ -88,6 +88,7 @@ def main():
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--start", type=int, default=0)
+    ap.add_argument("--dump", default=None, help="with --stats: save the raw (B,32) counters + losses as .npz")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     root = tempfile.mkdtemp(prefix="ihmr_sdfb_")
@@ -130,6 +131,8 @@ def main():
         torch.cuda.synchronize()
         st = stats.cpu().numpy().astype(np.float64)
         l = losses.cpu().numpy()
+        if args.dump:
+            np.savez_compressed(args.dump, stats=stats.cpu().numpy(), losses=l)
         rows = [(0, "voxels gridR"), (2, "voxels gridL"), (1, "rounds R"), (3, "rounds L"), (4, "activeQ gridR"), (5, "activeQ gridL"),
                 (6, "pairs"), (7, "candidates"), (8, "marked"), (9, "ray items"), (10, "passes"), (11, "ray in place"),
                 (12, "cand in place"), (16, "prep-done R"), (17, "prep-done L")]
