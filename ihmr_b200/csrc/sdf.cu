@@ -122,8 +122,7 @@ struct __align__(16) SdfSmem {
     float red[4 * SDF_WARPS];
     int region[4];              // lattice bounds of the marked columns: y min, y max, z min, z max
     int scan_warp[SDF_WARPS];
-    int qcnt[SDF_WARPS];        // fill of each warp's segment of the queue
-    int item;
+    uint32_t item;              // code of the next work item (frame * 2 + grid hand), 0xffffffff: none left
 };
 
 // (2i + 1 - G) / G; every intermediate is a small multiple of 1/G, so the fused form is exact too
@@ -473,19 +472,25 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
     const int n_items = bucket_end[SDF_BUCKETS - 1];
     float* spill = w.spill + (size_t)blockIdx.x * SDF_SPILL;
 
-    for (;;) {
-        __syncthreads();                       // the previous item is completely finished
-        if (tid == 0) s.item = (int)atomicAdd(&w.counters[SDF_BUCKETS], 1u);
-        __syncthreads();
-        if (s.item >= n_items) break;
-        uint32_t code;
-        {
-            const int t = s.item;
+    // thread 0 draws the ticket of the NEXT item (and looks its code up) while the current one is processed, so the
+    // round trips to the ticket counter and the item list are off the critical path
+    auto draw = [&]() {
+        const int t = (int)atomicAdd(&w.counters[SDF_BUCKETS], 1u);
+        uint32_t code = 0xffffffffu;               // no more items
+        if (t < n_items) {
             int k = 0, start = 0;
 #pragma unroll
             for (int q = 0; q + 1 < SDF_BUCKETS; ++q) if (t >= bucket_end[q]) { k = q + 1; start = bucket_end[q]; }
             code = w.items[(size_t)k * 2 * B + (t - start)];
         }
+        s.item = code;
+    };
+    if (tid == 0) draw();
+
+    for (;;) {
+        __syncthreads();                       // the previous item is completely finished; s.item is the next one
+        const uint32_t code = s.item;
+        if (code == 0xffffffffu) break;
         const int b = (int)(code >> 1), h = (int)(code & 1u), o = 1 - h;
         const ushort4* cl_tri = h ? cl_l : cl_r;
         uint16_t* hint = a.hints ? a.hints + ((size_t)b * 2 + h) * SDF_HINTS : nullptr;
@@ -505,23 +510,10 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
         };
         long long t_prev = clock64();
         const uint32_t lt_mask = (1u << lane) - 1u;
-        // every warp fills its own segment of s.queue (no atomics); after a barrier all threads walk the segments
-        auto for_each_queued = [&](auto&& fn) {
-            int pre[SDF_WARPS + 1];
-            pre[0] = 0;
-#pragma unroll
-            for (int w2 = 0; w2 < SDF_WARPS; ++w2) pre[w2 + 1] = pre[w2] + s.qcnt[w2];
-            for (int p2 = tid; p2 < pre[SDF_WARPS]; p2 += SDF_THREADS) {
-                int seg = 0, start = 0;
-#pragma unroll
-                for (int w2 = 1; w2 < SDF_WARPS; ++w2) if (p2 >= pre[w2]) { seg = w2; start = pre[w2]; }
-                fn(s.queue[seg * QSEG + (p2 - start)]);
-            }
-        };
-
         for (int i = tid; i < G * G; i += SDF_THREADS) { s.needed[i] = 0u; s.work[i] = 0u; }
         if (tid < 4) s.region[tid] = (tid & 1) ? -1 : G;
         __syncthreads();
+        if (tid == 0) draw();                  // (every thread has read s.item of this iteration)
 
         // ---- query vertices: normalised position, voxel corners, mark
         // (the cell of a query vertex is recomputed at sampling time rather than kept in registers)
@@ -673,7 +665,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             SDF_STAT(2)
             // ---- parity of the marked columns, two steps so that the ray tests run with full warps:
             //      (1) thread per face: lattice points inside its (y,z) box whose column is marked
-            //          -> (face, column) items; (2) thread per item: the exact ray test
+            //          -> (face, column) items in the warp's queue segment; (2) lane per item: the exact ray test
             const int ry0 = s.region[0], ry1 = s.region[1], rz0 = s.region[2], rz1 = s.region[3];
             uint32_t* rqueue = s.queue + warp * QSEG;
             int rq = 0;                                          // fill of this warp's segment (warp-uniform)
@@ -729,10 +721,12 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                     }
                 }
             }
-            if (lane == 0) s.qcnt[warp] = min(rq, QSEG);
             if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 9], rq);
-            __syncthreads();
-            for_each_queued([&](uint32_t e) { ray_item(s, cl_tri, (int)(e >> 10), (int)(e & 1023u)); });
+            __syncwarp();                // the ray tests by the warp that queued them: no block barrier in between
+            for (int p2 = lane; p2 < min(rq, QSEG); p2 += 32) {
+                const uint32_t e = rqueue[p2];
+                ray_item(s, cl_tri, (int)(e >> 10), (int)(e & 1023u));
+            }
             __syncthreads();
             if (stat) {                  // the new columns' parity words are known from now on
                 for (int c = tid; c < G * G; c += SDF_THREADS)
