@@ -23,7 +23,7 @@ HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "ihm
 # capacities of the penetration kernel so that ordinary frames take every multi-pass / overflow branch.
 VARIANTS = {
     "smallcaps": (os.path.join(OUT_DIR, "libihmr_b200_smallcaps.so"), "sdf.cu",
-                  ["-DSDF_PHI_CAP=64", "-DSDF_Q_CAP=128", "-DSDF_V_CHUNK=16"]),
+                  ["-DSDF_PHI_CAP=64", "-DSDF_Q_CAP=512"]),
 }
 
 NVCC_FLAGS = [

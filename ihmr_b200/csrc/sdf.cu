@@ -55,20 +55,19 @@ constexpr int SDF_CPT = G * G / SDF_THREADS;   // (z,y) columns per thread in th
 constexpr int SDF_SLOTS = (NV + SDF_THREADS - 1) / SDF_THREADS;   // query vertices per thread
 constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
 // Capacities (shared memory).  Everything beyond them is handled, not dropped: more voxels than
-// PHI_CAP -> further passes (finished values parked in a global spill area), a full candidate /
-// ray queue -> the item is processed in place.  tests build a variant with tiny capacities.
+// PHI_CAP -> further passes (finished values parked in a global spill area), a candidate / ray queue
+// segment that cannot take 32 more entries -> its entries are tested right away.  tests build a
+// variant with tiny capacities.
 #ifndef SDF_PHI_CAP
 #define SDF_PHI_CAP 1024            // voxels evaluated per pass
 #endif
 #ifndef SDF_Q_CAP
 #define SDF_Q_CAP 2304              // queued (voxel, face) candidates / (face, column) ray items
 #endif
-#ifndef SDF_V_CHUNK
-#define SDF_V_CHUNK 128             // voxels per search round
-#endif
-constexpr int PHI_CAP = SDF_PHI_CAP, Q_CAP = SDF_Q_CAP, V_CHUNK = SDF_V_CHUNK;
+constexpr int PHI_CAP = SDF_PHI_CAP, Q_CAP = SDF_Q_CAP;
 constexpr int QSEG = Q_CAP / SDF_WARPS;   // candidate queue segment of one warp
-static_assert(PHI_CAP <= 65536 && V_CHUNK >= 1, "queue entries pack the voxel index into 16 bits");
+static_assert(PHI_CAP <= 65536, "queue entries pack the voxel index into 16 bits");
+static_assert(QSEG >= 64, "a queue segment takes at least two rounds of 32 entries");
 constexpr int SDF_SPILL = NV * 8;   // a direction evaluates at most 8 voxels per query vertex
 constexpr int SDF_MAX_GRID = 160 * 8;
 constexpr int SDF_HINTS = 2048;     // nearest-face hints per (frame, direction): one u16 per voxel of an 8 x 16 x 16 block (wraps)
@@ -278,8 +277,19 @@ __device__ __forceinline__ void pair_test(SdfSmem& s, const ushort4* __restrict_
     if (bits < atomicMin(&s.best[vi], bits)) atomicExch(&s.hintw[vi], (uint32_t)slot);
 }
 
-// the same test out of line: the queue-full paths are rare and must not be inlined at every reservation site
-__device__ __noinline__ void pair_test_slow(SdfSmem& s, const ushort4* __restrict__ cl_tri, int vi, int slot) { pair_test(s, cl_tri, vi, slot); }
+// A warp's queue segment of (voxel, face) candidates, tested one per lane.  Out of line for the rare flush in the
+// middle of a voxel (segment nearly full); the flush at the end of a warp's voxels is inlined.
+__device__ __forceinline__ void pair_flush(SdfSmem& s, const ushort4* __restrict__ cl_tri, const uint32_t* wqueue, int n) {
+    __syncwarp();
+    for (int p2 = (int)(threadIdx.x & 31); p2 < n; p2 += 32) {
+        const uint32_t e = wqueue[p2];
+        pair_test(s, cl_tri, (int)(e >> 16), (int)(e & 0xffffu));
+    }
+    __syncwarp();
+}
+__device__ __noinline__ void pair_flush_slow(SdfSmem& s, const ushort4* __restrict__ cl_tri, const uint32_t* wqueue, int n) {
+    pair_flush(s, cl_tri, wqueue, n);
+}
 
 // one (face, column) item of the parity rasterisation: the exact ray test; a hit toggles the bits of all voxels whose
 // centre lies strictly left of the crossing
@@ -292,7 +302,17 @@ __device__ __forceinline__ void ray_item(SdfSmem& s, const ushort4* __restrict__
     while (cnt > 0 && !(x > voxel_center(cnt - 1))) --cnt;
     if (cnt > 0) atomicXor(&s.work[col], cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
 }
-__device__ __noinline__ void ray_item_slow(SdfSmem& s, const ushort4* __restrict__ cl_tri, int slot, int col) { ray_item(s, cl_tri, slot, col); }
+__device__ __forceinline__ void ray_flush(SdfSmem& s, const ushort4* __restrict__ cl_tri, const uint32_t* rqueue, int n) {
+    __syncwarp();
+    for (int p2 = (int)(threadIdx.x & 31); p2 < n; p2 += 32) {
+        const uint32_t e = rqueue[p2];
+        ray_item(s, cl_tri, (int)(e >> 10), (int)(e & 1023u));
+    }
+    __syncwarp();
+}
+__device__ __noinline__ void ray_flush_slow(SdfSmem& s, const ushort4* __restrict__ cl_tri, const uint32_t* rqueue, int n) {
+    ray_flush(s, cl_tri, rqueue, n);
+}
 
 // packed Q8 voxel centre -> index into the hint table: the low bits of (x, y, z), so that a block of
 // 8 x 16 x 16 neighbouring voxels never collides
@@ -450,8 +470,8 @@ __global__ void k_sdf_finish(int B, const float* __restrict__ parts, const float
     }
 // stats (B,32) int32, diagnostics only: [2h] voxels evaluated with grid hand h, [2h+1] search rounds,
 // [4+h] query vertices inside the grid box, [6] (voxel, cluster) pairs, [7] exact candidates, [8] marked voxels,
-// [9] ray items, [10] passes, [11] ray items processed in place (queue full), [12] candidates processed in
-// place (queue full), [16+h] direction finished by k_sdf_prep, [19..27] cycles per phase (mark, face boxes,
+// [9] ray items, [10] passes, [11] ray queue segments flushed early (full), [12] candidate queue segments flushed
+// early (full), [16+h] direction finished by k_sdf_prep, [19..27] cycles per phase (mark, face boxes,
 // parity, scan, worklist, seeds + candidates, exact tests, finish, sample + outputs)
 
 // kStatic = false compiles the static-grid cache out (stages in which both hands move)
@@ -668,7 +688,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             //          -> (face, column) items in the warp's queue segment; (2) lane per item: the exact ray test
             const int ry0 = s.region[0], ry1 = s.region[1], rz0 = s.region[2], rz1 = s.region[3];
             uint32_t* rqueue = s.queue + warp * QSEG;
-            int rq = 0;                                          // fill of this warp's segment (warp-uniform)
+            int rq = 0, nray = 0;                                // fill of this warp's segment (warp-uniform), items queued
             for (int c = warp; c < NCL; c += SDF_WARPS) {
                 {   // clusters that miss the (y,z) region of the marked columns are done
                     const uint2 cb = s.cl_box[c];
@@ -687,15 +707,14 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                 auto push = [&](bool ok, int face, int col) {          // warp-converged; the warp owns its queue segment
                     const uint32_t m = __ballot_sync(0xffffffffu, ok);
                     if (m == 0u) return;
-                    if (ok) {
-                        const int pos = rq + __popc(m & lt_mask);
-                        if (pos < QSEG) rqueue[pos] = ((uint32_t)face << 10) | (uint32_t)col;
-                        else {
-                            ray_item_slow(s, cl_tri, face, col);
-                            if (kStats) atomicAdd(&a.stats[b * 32 + 11], 1);
-                        }
+                    if (rq > QSEG - 32) {                              // no room for 32 more: test what is queued now
+                        ray_flush_slow(s, cl_tri, rqueue, rq);
+                        rq = 0;
+                        if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 11], 1);
                     }
+                    if (ok) rqueue[rq + __popc(m & lt_mask)] = ((uint32_t)face << 10) | (uint32_t)col;
                     rq += __popc(m);
+                    if (kStats) nray += __popc(m);
                 };
                 const bool cover = (j1 >= j0) && (k1 >= k0);
                 const bool small = cover && (j1 - j0 <= 1) && (k1 - k0 <= 1);
@@ -721,12 +740,8 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                     }
                 }
             }
-            if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 9], rq);
-            __syncwarp();                // the ray tests by the warp that queued them: no block barrier in between
-            for (int p2 = lane; p2 < min(rq, QSEG); p2 += 32) {
-                const uint32_t e = rqueue[p2];
-                ray_item(s, cl_tri, (int)(e >> 10), (int)(e & 1023u));
-            }
+            if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 9], nray);
+            ray_flush(s, cl_tri, rqueue, rq);     // the ray tests by the warp that queued them: no block barrier in between
             __syncthreads();
             if (stat) {                  // the new columns' parity words are known from now on
                 for (int c = tid; c < G * G; c += SDF_THREADS)
@@ -855,17 +870,16 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                 if (tid == 0) { atomicAdd(&a.stats[b * 32 + 2 * h], nvox); atomicAdd(&a.stats[b * 32 + 10], 1); }
             }
             SDF_STAT(5)
-            // ---- nearest face of every voxel.  Rounds of V_CHUNK voxels:
-            //   (B) warp per voxel: clusters whose box is closer than best (the cluster box is the union of the
-            //       face boxes, so it is never farther than any of them) -> their faces whose box is closer than
-            //       best -> (voxel, face) candidates.  A face that fails either test cannot be nearer than best.
-            //   (C) the same warp, lane per candidate of its own queue segment: exact point-triangle test, atomicMin into
-            //       the voxel.  No block barrier between the rounds.
-            for (int v0 = 0; v0 < nvox && any_todo; v0 += V_CHUNK) {
-                const int v1 = min(nvox, v0 + V_CHUNK);
+            // ---- nearest face of every voxel, one warp per voxel (round-robin), no block barrier:
+            //   (B) clusters whose box is closer than best (the cluster box is the union of the face boxes, so it is
+            //       never farther than any of them) -> their faces whose box is closer than best -> (voxel, face)
+            //       candidates in the warp's queue segment.  A face that fails either test cannot be nearer than best.
+            //   (C) lane per candidate: exact point-triangle test, atomicMin into the voxel; when the warp has no
+            //       voxels left, or earlier when the segment cannot take 32 more entries.
+            if (any_todo) {
                 uint32_t* wqueue = s.queue + warp * QSEG;      // candidates of this warp's voxels: no atomics
                 int wq = 0, ncand = 0;                           // fill (warp-uniform), candidates found
-                for (int v = v0 + warp; v < v1; v += SDF_WARPS) {
+                for (int v = warp; v < nvox; v += SDF_WARPS) {
                     const int seed = (int)s.hintw[v];
                     if (stat && seed == (int)HINT_DONE) continue;
                     const uint32_t q = s.worklist[v];
@@ -877,32 +891,25 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
                     if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 6], __popc(m0) + __popc(m1));
                     const uint32_t ventry = ((uint32_t)v << 16) | (uint32_t)lane;
                     auto cluster = [&](int c) {
+                        if (wq > QSEG - 32) {                  // warp-uniform
+                            pair_flush_slow(s, cl_tri, wqueue, wq);
+                            wq = 0;
+                            if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 12], 1);
+                        }
                         const int slot = c * 32 + lane;
                         const uint2 fb = s.fbox[slot];
                         const bool ok = qbox_4d2(fb, q) < thr && slot != seed && fb.x < (1u << 24);      // (not an empty table slot)
                         const uint32_t okm = __ballot_sync(0xffffffffu, ok);
-                        const int n = __popc(okm);
-                        if (wq + n <= QSEG) {                 // warp-uniform
-                            if (ok) wqueue[wq + __popc(okm & lt_mask)] = ventry + ((uint32_t)c << 5);
-                            wq += n;
-                        } else if (ok) {
-                            pair_test_slow(s, cl_tri, v, slot);     // does not fit the segment: test in place
-                            if (kStats) atomicAdd(&a.stats[b * 32 + 12], 1);
-                        }
-                        ncand += n;
+                        const int pos = wq + __popc(okm & lt_mask);
+                        if (ok) wqueue[pos] = ventry + ((uint32_t)c << 5);
+                        wq += __popc(okm);
+                        if (kStats) ncand += __popc(okm);
                     };
                     for (uint32_t mm = m0; mm; mm &= mm - 1u) cluster(__ffs(mm) - 1);
                     for (uint32_t mm = m1; mm; mm &= mm - 1u) cluster(__ffs(mm) + 31);
                 }
-                // (C) by the same warp on its own segment: no block barrier between the rounds
-                __syncwarp();
-                for (int p2 = lane; p2 < wq; p2 += 32) {
-                    const uint32_t e = wqueue[p2];
-                    pair_test(s, cl_tri, (int)(e >> 16), (int)(e & 0xffffu));
-                }
-                __syncwarp();
+                pair_flush(s, cl_tri, wqueue, wq);
                 if (kStats && lane == 0) atomicAdd(&a.stats[b * 32 + 7], ncand);
-                if (kStats && tid == 0) atomicAdd(&a.stats[b * 32 + 2 * h + 1], 1);
             }
             __syncthreads();
             SDF_STAT(7)

@@ -115,12 +115,12 @@ int ihmr_sdf_loss_exact(const ihmr_model_t* model, int n_frames, const float* ha
                         size_t workspace_bytes, ihmr_stream_t stream);
 
 /* Diagnostic variant for tools/tests: same kernels, additionally fills stats (n,32) int32 (zeroed
- * by the caller): per grid hand h in {0,1}: [2h] voxels evaluated, [2h+1] search rounds, [4+h] query
- * vertices inside the grid box, [16+h] direction finished by the prep kernel (boxes cannot meet);
+ * by the caller): per grid hand h in {0,1}: [2h] voxels evaluated, [4+h] query vertices inside the
+ * grid box, [16+h] direction finished by the prep kernel (boxes cannot meet);
  * [6] (voxel, cluster) pairs, [7] exact candidates, [8] marked voxels, [9] ray items, [10] passes,
- * [11] / [12] ray items / candidates processed in place because the shared-memory queue was full,
- * [19..27] SM cycles thread 0 spent per phase (mark, face boxes, parity, scan, worklist,
- * seeds + candidates, exact tests, finish, sample + outputs). */
+ * [11] / [12] ray / candidate queue segments tested early because they could not take 32 more entries,
+ * [19..27] SM cycles thread 0 spent per phase (mark, face boxes, parity, scan, worklist + seeds,
+ * unused, candidate search + exact tests, finish, sample + outputs). */
 int ihmr_sdf_stats(const ihmr_model_t* model, int n_frames, const float* hand_verts, float* losses,
                    int32_t* stats, void* workspace, size_t workspace_bytes, ihmr_stream_t stream);
 

@@ -121,8 +121,8 @@ def main():
         searching = (st[:, 0] > 0).astype(np.int64) + (st[:, 2] > 0)
         print(json.dumps({"what": "stats", "frames": B, "voxels": int(st[:, 0].sum() + st[:, 2].sum()), "passes": int(st[:, 10].sum()),
                           "max_passes_per_direction": int(np.max(st[:, 10] - np.maximum(searching - 1, 0))) if B else 0,
-                          "rounds": int(st[:, 1].sum() + st[:, 3].sum()), "candidates": int(st[:, 7].sum()),
-                          "rays_in_place": int(st[:, 11].sum()), "candidates_in_place": int(st[:, 12].sum()),
+                          "candidates": int(st[:, 7].sum()),
+                          "ray_flushes": int(st[:, 11].sum()), "candidate_flushes": int(st[:, 12].sum()),
                           "prep_done_directions": int(st[:, 16].sum() + st[:, 17].sum())}), flush=True)
 
     if args.stats:
@@ -133,9 +133,9 @@ def main():
         l = losses.cpu().numpy()
         if args.dump:
             np.savez_compressed(args.dump, stats=stats.cpu().numpy(), losses=l)
-        rows = [(0, "voxels gridR"), (2, "voxels gridL"), (1, "rounds R"), (3, "rounds L"), (4, "activeQ gridR"), (5, "activeQ gridL"),
-                (6, "pairs"), (7, "candidates"), (8, "marked"), (9, "ray items"), (10, "passes"), (11, "ray in place"),
-                (12, "cand in place"), (16, "prep-done R"), (17, "prep-done L")]
+        rows = [(0, "voxels gridR"), (2, "voxels gridL"), (4, "activeQ gridR"), (5, "activeQ gridL"),
+                (6, "pairs"), (7, "candidates"), (8, "marked"), (9, "ray items"), (10, "passes"), (11, "ray flushes"),
+                (12, "cand flushes"), (16, "prep-done R"), (17, "prep-done L")]
         for i, n in rows:
             c = st[:, i]
             print(f"{n:>16}: mean {c.mean():9.1f}  p50 {np.percentile(c, 50):7.0f} p90 {np.percentile(c, 90):8.0f} "
