@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("IHMR_B200_LIB", os.path.join(_HERE, "_lib", "libihmr_
 
 EXPORTS = (
     "ihmr_last_error", "ihmr_abi_version", "ihmr_model_create", "ihmr_model_destroy",
-    "ihmr_model_update_shapedirs", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
+    "ihmr_model_update_shapedirs", "ihmr_model_set_sdf_conventions", "ihmr_mano_workspace_bytes", "ihmr_mano_forward",
     "ihmr_mano_backward", "ihmr_sdf_workspace_bytes", "ihmr_sdf_loss", "ihmr_sdf_loss_exact", "ihmr_opt_workspace_bytes", "ihmr_opt_stage",
     "ihmr_opt_final", "ihmr_opt_value_and_grad", "ihmr_launch_count", "ihmr_opt_profile_iteration", "ihmr_sdf_stats", "ihmr_gemm_tf32x3", "ihmr_gemm_reference_fp32", "ihmr_eval_metrics", "ihmr_measure_fp32_peak", "ihmr_select_snapshots", "ihmr_opt_criteria", "ihmr_mlp_input", "ihmr_linear", "ihmr_mlp_apply", "ihmr_select_better",
 )
@@ -76,6 +76,8 @@ def load() -> C.CDLL:
     lib.ihmr_model_destroy.argtypes = [vp]
     lib.ihmr_model_update_shapedirs.restype = i32
     lib.ihmr_model_update_shapedirs.argtypes = [vp, vp, vp]
+    lib.ihmr_model_set_sdf_conventions.restype = i32
+    lib.ihmr_model_set_sdf_conventions.argtypes = [vp, C.c_float, i32]
     lib.ihmr_mano_workspace_bytes.restype = sz
     lib.ihmr_mano_workspace_bytes.argtypes = [i32]
     lib.ihmr_mano_forward.restype = i32

@@ -167,6 +167,8 @@ int ihmr_model_create(const float* v_template, const float* shapedirs, const flo
 
     ihmr_model* m = new ihmr_model();
     memset(m, 0, sizeof(*m));
+    m->sdf_box_scale = 0.6f;          // (1 + 0.2) / 2, +x parity ray: ihmr_model_set_sdf_conventions changes them
+    m->sdf_ray_axis = 0;
     m->device = device;
     m->num_sms = prop.multiProcessorCount;
     for (int j = 0; j < NJ; ++j) m->parents[j] = parents[j];
@@ -217,6 +219,13 @@ void ihmr_model_destroy(ihmr_model_t* m) {
     cudaFree(m->Wt); cudaFree(m->W4); cudaFree(m->hands_mean); cudaFree(m->Jreg); cudaFree(m->Sv);
     cudaFree(m->faces[0]); cudaFree(m->faces[1]); cudaFree(m->cl_tri[0]); cudaFree(m->cl_tri[1]);
     delete m;
+}
+
+int ihmr_model_set_sdf_conventions(ihmr_model_t* m, float scale_factor, int ray_axis) {
+    IHMR_CHECK_ARG(m && scale_factor > -1.0f && scale_factor < 10.0f && ray_axis >= 0 && ray_axis <= 2);
+    m->sdf_box_scale = (1.0f + scale_factor) * 0.5f;
+    m->sdf_ray_axis = ray_axis;
+    return IHMR_OK;
 }
 
 int ihmr_model_update_shapedirs(ihmr_model_t* m, const float* shapedirs, ihmr_stream_t stream) {

@@ -80,4 +80,6 @@ struct ihmr_model {
     uint16_t* faces[2];  // (1538, 4) u16 per hand (right, left), 4th lane unused
     uint16_t* cl_tri[2]; // (49 clusters x 32, 4) u16: vertex ids of the faces of each spatial cluster, lane 3 = valid
     int parents[16];
+    float sdf_box_scale = 0.6f;   // penetration-field conventions (ihmr_model_set_sdf_conventions): (1 + scale_factor) / 2
+    int sdf_ray_axis = 0;         // and the axis of the inside/outside parity ray
 };

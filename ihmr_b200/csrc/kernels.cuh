@@ -105,6 +105,8 @@ struct SdfArgs {
     float* phic = nullptr;             // (B, 2048) or null: finished voxel distances beside the hint table (no init needed)
     void* ws = nullptr;                // sdf_ws_bytes(B) of scratch: frame headers, work list, loss parts, spill area
     float* losses = nullptr;           // (B) or null: mask * (part_0 + part_1) / 4 (one more tiny launch)
+    float box_scale = 0.6f;            // (filled by launch_sdf from the model) scale = box_scale * max bbox extent   (A2)
+    int ray_axis = 0;                  // (filled by launch_sdf from the model) world axis of the parity ray          (A4)
 };
 size_t sdf_ws_bytes(int B);
 size_t sdf_hint_bytes(int B);

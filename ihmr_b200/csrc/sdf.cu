@@ -186,6 +186,19 @@ __device__ __forceinline__ float pt_tri_dist2(const float* p, const float* a, co
     return (va >= 0.f && vb >= 0.f && vc >= 0.f) ? fminf(best, din) : best;
 }
 
+// Ray axis (assumption A4): the kernels work in coordinates whose first component runs along the parity ray.
+// world (w0,w1,w2) -> internal (w[axis], w[axis+1], w[axis+2]) (cyclic), and back for the gradients.
+__device__ __forceinline__ void to_ray_frame(float* v, int axis) {
+    if (axis == 0) return;
+    const float a0 = v[0], a1 = v[1], a2 = v[2];
+    if (axis == 1) { v[0] = a1; v[1] = a2; v[2] = a0; } else { v[0] = a2; v[1] = a0; v[2] = a1; }
+}
+__device__ __forceinline__ void from_ray_frame(float* v, int axis) {
+    if (axis == 0) return;
+    const float a0 = v[0], a1 = v[1], a2 = v[2];
+    if (axis == 1) { v[0] = a2; v[1] = a0; v[2] = a1; } else { v[0] = a1; v[1] = a2; v[2] = a0; }
+}
+
 // floats <-> integers with the same ordering (an involution on the bit pattern)
 __device__ __forceinline__ int float_ordered(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
@@ -386,14 +399,16 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) k_sdf_prep(int B, SdfArgs a, 
             lo[1][1] += sh[1]; hi[1][1] += sh[1];
             lo[1][2] += sh[2]; hi[1][2] += sh[2];
         }
-        // Appendix B: centre = box midpoint, scale = 0.6 * max extent   ((1 + 0.2) * 0.5)
+        to_ray_frame(lo[0], a.ray_axis); to_ray_frame(hi[0], a.ray_axis);
+        to_ray_frame(lo[1], a.ray_axis); to_ray_frame(hi[1], a.ray_axis);
+        // Appendix B: centre = box midpoint, scale = (1 + scale_factor) * 0.5 * max extent   (A2; 0.6 by default)
         float dp[2][16];
 #pragma unroll
         for (int hnd = 0; hnd < 2; ++hnd) {
             float cen[3], ext = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) { cen[c] = (lo[hnd][c] + hi[hnd][c]) * 0.5f; ext = fmaxf(ext, hi[hnd][c] - lo[hnd][c]); }
-            const float scale = 0.6f * ext;
+            const float scale = a.box_scale * ext;
             dp[hnd][3] = scale;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -527,6 +542,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             const float* p = a.verts + (((size_t)b * 2 + hand) * NV + v) * 3;
             out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
             if (xform && hand == 1) { out[0] = -out[0] + shx; out[1] += shy; out[2] += shz; }
+            to_ray_frame(out, a.ray_axis);
         };
         long long t_prev = clock64();
         const uint32_t lt_mask = (1u << lane) - 1u;
@@ -995,6 +1011,7 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
             if (a.gverts || a.gshift) {
                 const float kk = kbase * drho;
                 float g[3] = {kk * acc[1], kk * acc[2], kk * acc[3]};
+                from_ray_frame(g, a.ray_axis);
                 sums[1] += g[0]; sums[2] += g[1]; sums[3] += g[2];
                 if (a.gverts) {
                     if (xform && o == 1) g[0] = -g[0];
@@ -1099,6 +1116,7 @@ k_sdf_exact(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const u
             const float* p = a.verts + (((size_t)b * 2 + hand) * NV + v) * 3;
             out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
             if (xform && hand == 1) { out[0] = -out[0] + shx; out[1] += shy; out[2] += shz; }
+            to_ray_frame(out, a.ray_axis);
         };
         // ---- query vertices that can be inside at all: within the mesh's (y,z) extent and not right of its largest x
         for (int v = tid; v < NV; v += SDF_THREADS) {
@@ -1231,6 +1249,7 @@ k_sdf_exact(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const u
             if (a.per_vert) a.per_vert[ov0 + v] = r.x;
             if (a.origin) a.origin[ov0 + v] = r.x * scale;
             float g[3] = {kbase * r.y, kbase * r.z, kbase * r.w};
+            from_ray_frame(g, a.ray_axis);
             sums[1] += g[0]; sums[2] += g[1]; sums[3] += g[2];
             if (a.gverts) {
                 if (xform && o == 1) g[0] = -g[0];
@@ -1260,6 +1279,7 @@ int launch_sdf_exact(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t 
     IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, (SDF_BUCKETS + 1) * 4, st));
     SdfArgs pa = a;
     pa.gzero = nullptr;                 // (the skipped directions get explicit zeros in this mode)
+    pa.box_scale = m->sdf_box_scale; pa.ray_axis = m->sdf_ray_axis;
     k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, pa, w);
     IHMR_LAUNCH_OK();
     const int grid = std::min(std::min(m->num_sms * ctas_per_sm, SDF_MAX_GRID), 2 * B);
@@ -1290,10 +1310,12 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     }
     const SdfWs w = sdf_ws_carve(a.ws, B);
     IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, (SDF_BUCKETS + 1) * 4, st));
-    k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, a, w);
+    SdfArgs pa = a;
+    pa.box_scale = m->sdf_box_scale; pa.ray_axis = m->sdf_ray_axis;       // conventions A2 / A4 of the model
+    k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, pa, w);
     IHMR_LAUNCH_OK();
     const int grid = std::min(std::min(m->num_sms * ctas_per_sm[kv], SDF_MAX_GRID), 2 * B);
-    kernel<<<grid, SDF_THREADS, sizeof(SdfSmem), st>>>(B, a, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
+    kernel<<<grid, SDF_THREADS, sizeof(SdfSmem), st>>>(B, pa, w, reinterpret_cast<const ushort4*>(m->cl_tri[0]),
                                                        reinterpret_cast<const ushort4*>(m->cl_tri[1]));
     IHMR_LAUNCH_OK();
     if (a.losses) {

@@ -56,6 +56,17 @@ class DeviceModel:
         _lib.check(lib.ihmr_model_create(*[a.ctypes.data_as(C.c_void_p) for a in self._keep], int(device),
                                          C.byref(handle)), "ihmr_model_create")
         self.handle, self.device, self._lib = handle, int(device), lib
+        self._sdf_conventions = (0.2, 0)
+
+    def set_sdf_conventions(self, scale_factor: float = 0.2, ray_axis: int = 0):
+        """Box scale factor and parity-ray axis of the penetration field for every later
+        penetration call on this handle.  Not stream ordered: pending work on other streams is synchronised first."""
+        conv = (float(scale_factor), int(ray_axis))
+        if conv != self._sdf_conventions:
+            torch.cuda.synchronize(self.device)
+            _lib.check(self._lib.ihmr_model_set_sdf_conventions(self.handle, C.c_float(conv[0]), conv[1]),
+                       "ihmr_model_set_sdf_conventions")
+            self._sdf_conventions = conv
 
     def update_shapedirs(self, shapedirs: np.ndarray):
         sd = np.ascontiguousarray(np.asarray(shapedirs, dtype=np.float32).reshape(778, 3, 10))

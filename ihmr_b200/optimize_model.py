@@ -129,6 +129,9 @@ class OptimizeModel:
         if torch.mean(torch.abs(sl[:, 0, :] - sr[:, 0, :])) < 1e-7:
             sl[:, 0, :] *= -1
         self._model = self._build_device_model()
+        # conventions of the un-vendored `sdf` package the oracle had to assume; the
+        # reference call site (loss_utils.py:181-182) uses the package defaults
+        self._model.set_sdf_conventions(getattr(opt, "sdf_scale_factor", 0.2), getattr(opt, "sdf_ray_axis", 0))
 
         self.strategy = strategies[opt.strategy] if isinstance(opt.strategy, str) else opt.strategy
         self.default_loss_weights = dict(DEFAULT_LOSS_WEIGHTS)

@@ -23,12 +23,13 @@ from .mano_layer import DeviceModel, _f32c, _ptr, _stream, faces_only_model
 
 class _SdfFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, hand_verts):
+    def forward(ctx, module, hand_verts, scale_factor):
         hv = _f32c(hand_verts)
         if hv.dim() != 4 or tuple(hv.shape[1:]) != (2, 778, 3):
             raise ValueError("hand_verts must be (B,2,778,3)")
         B, dev = hv.shape[0], hv.device
         model = module._device_model(dev)
+        model.set_sdf_conventions(scale_factor, module.ray_axis)
         losses = torch.empty(B, device=dev, dtype=torch.float32)
         per_vert = torch.empty(B, 1556, device=dev, dtype=torch.float32)
         origin = torch.empty(B, 1556, device=dev, dtype=torch.float32)
@@ -49,13 +50,18 @@ class _SdfFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_losses, _g_pv, _g_or):
         if ctx.grad is None:
-            return None, None
-        return None, ctx.grad * g_losses.view(-1, 1, 1, 1)
+            return None, None, None
+        return None, ctx.grad * g_losses.view(-1, 1, 1, 1), None
 
 
 class SDFLoss(nn.Module):
-    def __init__(self, faces_right, faces_left, grid_size=32, robustifier=None, debugging=False):
+    def __init__(self, faces_right, faces_left, grid_size=32, robustifier=None, debugging=False, ray_axis=0):
+        """``ray_axis`` (not a reference argument): world axis of the inside/outside parity ray, assumption A4 of
+        SURVEY.md §8(c); 0 = +x is what the oracle restates."""
         super().__init__()
+        if ray_axis not in (0, 1, 2):
+            raise ValueError("ray_axis must be 0, 1 or 2")
+        self.ray_axis = int(ray_axis)
         if grid_size != 32:
             raise ValueError("the penetration kernel is built for the reference's 32^3 grid (A1)")
         self.faces_right = np.asarray(faces_right).astype(np.int32)
@@ -72,8 +78,8 @@ class SDFLoss(nn.Module):
             self._models[idx] = faces_only_model(self.faces_right, self.faces_left, idx)
         return self._models[idx]
 
-    def forward(self, hand_verts, return_per_vert_loss=False, return_origin_scale_loss=False, **_):
-        losses, per_vert, origin = _SdfFn.apply(self, hand_verts)
+    def forward(self, hand_verts, return_per_vert_loss=False, return_origin_scale_loss=False, scale_factor=0.2):
+        losses, per_vert, origin = _SdfFn.apply(self, hand_verts, float(scale_factor))
         if return_per_vert_loss and return_origin_scale_loss:
             return losses, per_vert, origin
         if return_per_vert_loss:
@@ -90,10 +96,10 @@ class SDFLossExact(SDFLoss):
     reference-parity module."""
     exact = True
 
-    def __init__(self, faces_right, faces_left, grid_size=32, robustifier=None, debugging=False):
+    def __init__(self, faces_right, faces_left, grid_size=32, robustifier=None, debugging=False, ray_axis=0):
         if robustifier:
             raise ValueError("the exact mode has no robustifier")
-        super().__init__(faces_right, faces_left, grid_size, None, debugging)
+        super().__init__(faces_right, faces_left, grid_size, None, debugging, ray_axis)
 
 
 class SDFLoss_Single(SDFLoss):

@@ -15,7 +15,7 @@
  *   - return value 0 = ok, negative = error (IHMR_E_*); the message of the last error on the
  *     calling thread is returned by ihmr_last_error(); no C++ exception crosses the ABI;
  *   - re-entrant; a model handle is immutable after creation (except
- *     ihmr_model_update_shapedirs) and may be shared by threads using different streams;
+ *     ihmr_model_update_shapedirs / ihmr_model_set_sdf_conventions) and may be shared by threads using different streams;
  *   - sm_100a only, no CPU fallback: on any other device ihmr_model_create fails.
  */
 #ifndef IHMR_B200_H
@@ -64,6 +64,12 @@ void ihmr_model_destroy(ihmr_model_t* model);
 /* The reference mutates `.shapedirs` of a loaded model in place (optimize_model.py:109-113);
  * the L0 layer re-uploads through this call when its tensor changed.  shapedirs: HOST (778,3,10). */
 int ihmr_model_update_shapedirs(ihmr_model_t* model, const float* shapedirs, ihmr_stream_t stream);
+/* Conventions of the penetration field the upstream `sdf` package (un-vendored, unpinned) may hold differently
+ * (SURVEY.md §8(c) A2, A4): the box scale is (1 + scale_factor) * 0.5 * max extent (`SDFLoss.forward(...,
+ * scale_factor=0.2)` at the call site src/models/loss_utils.py:181-182 uses the default) and the axis of the
+ * inside/outside parity ray (0 = +x).  Defaults 0.2 and 0; applies to every later penetration call on this model.
+ * Not stream ordered: call it before enqueuing work that should see the change. */
+int ihmr_model_set_sdf_conventions(ihmr_model_t* model, float scale_factor, int ray_axis);
 
 /* ---- MANO layer (a4) ------------------------------------------------------------------
  * Replaces `mano_models['right'](global_orient=, hand_pose=, betas=)` -> .vertices/.joints at

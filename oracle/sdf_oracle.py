@@ -119,8 +119,12 @@ def sdf_grid_numpy(verts: np.ndarray, faces: np.ndarray, grid_size: int) -> np.n
 class SDFLoss(nn.Module):
     """Restatement of sdf.SDFLoss for two hands (Appendix B of SURVEY.md)."""
 
-    def __init__(self, faces_right, faces_left, grid_size=32, robustifier=None, debugging=False):
+    def __init__(self, faces_right, faces_left, grid_size=32, robustifier=None, debugging=False, ray_axis=0):
         super().__init__()
+        # A4 audit knob (not a reference argument): world axis of the parity ray.  The field, the boxes and the
+        # trilinear sampling are symmetric under a cyclic permutation of the coordinates, so a ray along axis a is
+        # the +x statement below applied to (w[a], w[a+1], w[a+2]).
+        self.ray_axis = int(ray_axis)
         self.register_buffer("faces_right", torch.tensor(np.asarray(faces_right).astype(np.int32)))
         self.register_buffer("faces_left", torch.tensor(np.asarray(faces_left).astype(np.int32)))
         self.grid_size = grid_size
@@ -145,6 +149,8 @@ class SDFLoss(nn.Module):
     def forward(self, hand_verts, return_per_vert_loss=False, return_origin_scale_loss=False,
                 scale_factor=0.2):
         B = hand_verts.shape[0]
+        if self.ray_axis:
+            hand_verts = hand_verts[..., [(self.ray_axis + c) % 3 for c in range(3)]]
         center, scale = self.boxes(hand_verts, scale_factor)
         phi = self.grids(hand_verts, center, scale)
         psi = [None, None]                                 # psi[o] = hand o sampled in the other grid

@@ -27,11 +27,11 @@ def load_golden(name):
     return data, out, int(z["epochs"]), int(z["save_mid_freq"])
 
 
-def oracle_loop(layers, B, epochs, freq, bs_norm=None, dtype=torch.float32):
+def oracle_loop(layers, B, epochs, freq, bs_norm=None, dtype=torch.float32, ray_axis=0):
     right, left = layers
     if dtype != torch.float32:
         right, left = right.double(), left.double()
-    sdf = sdf_oracle.SDFLoss(right.faces, left.faces)
+    sdf = sdf_oracle.SDFLoss(right.faces, left.faces, ray_axis=ray_axis)
     return HL.HostLoopOracle(right, right.faces, left.faces, sdf, B, strategy=HL.opt_default_strategy(epochs),
                              save_mid_freq=freq, bs_norm=bs_norm, dtype=dtype)
 

@@ -133,6 +133,38 @@ def test_sdf_vs_oracle(cuda_layers, oracle_layers, mode, start, count):
     assert float((hv.grad.cpu() - hv_cpu.grad).abs().max()) <= REL_TOL * gscale + 1e-9
 
 
+@pytest.mark.parametrize("scale_factor,ray_axis", [(0.2, 1), (0.2, 2), (0.35, 0), (0.1, 2)])
+def test_sdf_conventions_flip_together_with_the_oracle(cuda_layers, oracle_layers, scale_factor, ray_axis):
+    """The two assumptions about the un-vendored `sdf` package that are parameters on both sides (box
+    scale factor, A4: axis of the inside/outside parity ray): changed in the oracle and in the kernels together the
+    results still agree, and they differ from the default convention's (so the switch really reaches the kernels)."""
+    from ihmr_b200 import sdf_loss, synthetic
+    from oracle import mano_oracle, sdf_oracle
+    frames = []
+    for mode, start, count in (("collision", 8, 5), ("typical", 300, 7)):
+        raw = synthetic.make_raw_frames(start, count, seed=0, mode=mode)
+        with torch.no_grad():
+            rv, lv, _ = mano_oracle.two_hand_forward(oracle_layers[0], torch.tensor(raw["true_pose"]),
+                                                     torch.tensor(raw["true_shape"]), torch.tensor(raw["true_trans"]))
+        frames.append(torch.stack([rv, lv], 1))
+    hv_cpu = torch.cat(frames).clone().requires_grad_(True)
+    ref = sdf_oracle.SDFLoss(oracle_layers[0].faces, oracle_layers[1].faces, ray_axis=ray_axis)
+    l_ref, pv_ref, o_ref = ref(hv_cpu, True, True, scale_factor=scale_factor)
+    l_ref.sum().backward()
+    hv = hv_cpu.detach().cuda().requires_grad_(True)
+    mod = sdf_loss.SDFLoss(cuda_layers[0].faces, cuda_layers[1].faces, ray_axis=ray_axis).cuda()
+    l, pv, o = mod(hv, return_per_vert_loss=True, return_origin_scale_loss=True, scale_factor=scale_factor)
+    l.sum().backward()
+    scale = max(float(l_ref.abs().max()), 1e-12)
+    assert float(l_ref.abs().max()) > 0
+    assert float((l.detach().cpu() - l_ref.detach()).abs().max()) <= REL_TOL * scale + 1e-9
+    assert float((o.cpu() - o_ref).abs().max()) <= 2e-6
+    gscale = max(float(hv_cpu.grad.abs().max()), 1e-12)
+    assert float((hv.grad.cpu() - hv_cpu.grad).abs().max()) <= REL_TOL * gscale + 1e-9
+    l_def = _cuda_sdf(cuda_layers)(hv.detach())
+    assert float((l_def.cpu() - l.detach().cpu()).abs().max()) > 1e-3 * scale
+
+
 def test_sdf_disjoint_hands_is_exact_zero(cuda_layers):
     orient, pose, betas = random_hands(4, seed=3)
     v = cuda_layers[0](global_orient=orient.cuda(), hand_pose=pose.cuda(), betas=betas.cuda()).vertices
@@ -183,6 +215,43 @@ def test_value_and_grad_vs_oracle(model_root, oracle_layers, stage_id, mode):
               "l_pose": slice(57, 102), "r_shape": slice(102, 112), "l_shape": slice(112, 122)}
     for name, sl in groups.items():
         assert rel_err(grad[:, sl], ref_grad[:, sl]) <= REL_TOL, name
+
+
+@pytest.mark.parametrize("stage_id", [0, 2])
+def test_value_and_grad_under_another_ray_axis(model_root, oracle_layers, stage_id):
+    """One fused iteration (losses + parameter gradients) with the parity ray along +y in the oracle loop and in the
+    CUDA loop (`opt.sdf_ray_axis`): the convention travels through the stage kernels, the stage-0 shortcut included."""
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default
+    B = 3
+    batch = H.torch_batch(H.make_batch(oracle_layers[0], 0, B, mode="collision"))
+    stage = opt_default[stage_id]
+    hl = H.oracle_loop(oracle_layers, B, 1, 1, ray_axis=1)
+    hl.set_input(batch)
+    hl.init_optimize()
+    for k in hl.p:
+        hl.p[k] = hl.p[k].detach().clone().requires_grad_(True)
+    hl.forward()
+    hl.compute_loss(stage["loss_weights"])
+    hl.loss.backward()
+    ref_grad = torch.cat([torch.zeros(B, 3), hl.p["pred_hand_trans"].grad.view(B, 3), hl.p["pred_right_orient"].grad,
+                          hl.p["pred_right_pose_params"].grad, hl.p["pred_left_orient"].grad,
+                          hl.p["pred_left_pose_params"].grad, hl.p["pred_right_shape_params"].grad,
+                          hl.p["pred_left_shape_params"].grad], 1).numpy()
+    opt = H.make_opt(model_root, B)
+    opt.sdf_ray_axis = 1
+    model = OptimizeModel(opt)
+    model.set_input(batch)
+    model.init_optimize()
+    losses, grad = model.value_and_grad(stage)
+    losses, grad = losses.cpu().numpy(), grad.cpu().numpy()
+    r = float(hl.collision_loss)
+    assert r > 0 and abs(losses[3] - r) <= REL_TOL * abs(r), (losses[3], r)
+    live = {0: slice(3, 6), 2: slice(9, 54)}[stage_id]
+    assert rel_err(grad[:, live], ref_grad[:, live]) <= REL_TOL
+    ref_x = H.oracle_loop(oracle_layers, B, 1, 1)
+    ref_x.set_input(batch); ref_x.init_optimize(); ref_x.forward(); ref_x.compute_loss(stage["loss_weights"])
+    assert abs(float(ref_x.collision_loss) - r) > 1e-3 * abs(r)          # the +x convention gives another value
 
 
 # ------------------------------------------------------------------------- whole loop
