@@ -469,8 +469,12 @@ size_t opt_ws_bytes(int B) { return opt_ws_layout(nullptr, B, nullptr); }
 // recorded on the stream after each kernel class.  Off on the normal path.
 constexpr int N_KERNEL_CLASSES = 9;   // pose_prep blend_fwd skin_fwd sdf frame_loss skin_bwd blend_bwd pose_bwd step
 struct IterProf {
-    cudaEvent_t ev[N_KERNEL_CLASSES + 1];
-    cudaStream_t st;
+    cudaEvent_t ev[N_KERNEL_CLASSES + 1] = {};
+    cudaStream_t st = nullptr;
+    IterProf() = default;
+    IterProf(const IterProf&) = delete;
+    IterProf& operator=(const IterProf&) = delete;
+    ~IterProf() { for (auto& e : ev) if (e) cudaEventDestroy(e); }      // every return path releases the events
     void tick(int i) { cudaEventRecord(ev[i], st); }
 };
 #define IHMR_TICK(prof, i) do { if (prof) (prof)->tick(i); } while (0)
@@ -523,6 +527,14 @@ struct IterPlan {
                               // 2 = later iterations (affine in beta); backward is the affine one in both
 };
 
+// Which kernels an iteration needs, from the parameter groups the stage updates.
+// Dependency on the oracle's reading of the un-vendored `sdf` package (unpinned): the skipped
+// direction below (sdf_skip_grid = 2 when only pred_hand_trans is live and no snapshot is due) is the one whose grid
+// hand is the LEFT hand; its samples are the right hand's vertices, which do not move, and its box centre / scale are
+// built under no_grad (A2) like the field itself (A5), so it carries no gradient to pred_hand_trans and only its
+// VALUE is needed, at snapshots.  If the real package lets gradients through the box centre or scale, the trans-stage
+// gradient differs: set IHMR_STAGE_GENERIC_KERNELS in ihmr_stage_t.flags (every stage on the generic chain, both
+// directions every iteration) and extend the penetration backward accordingly.
 static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot, bool generic) {
     const bool live_blend = mask & (IHMR_P_R_POSE | IHMR_P_L_POSE | IHMR_P_R_SHAPE | IHMR_P_L_SHAPE);
     const bool live_mano = live_blend || (mask & (IHMR_P_R_ORIENT | IHMR_P_L_ORIENT));
@@ -531,7 +543,7 @@ static IterPlan plan_iteration(uint32_t mask, bool first, bool snapshot, bool ge
     p.blend_fwd = first || live_blend;
     p.mano_bwd = live_mano;
     p.blend_bwd = live_blend;
-    p.sdf_skip_grid = (!live_mano && !snapshot) ? 2 : 0;
+    p.sdf_skip_grid = (!live_mano && !snapshot && !generic) ? 2 : 0;
     p.dense_grad = generic;
     p.static_right = !live_mano && !generic;
     if (generic) return p;      // IHMR_STAGE_GENERIC_KERNELS: every stage on the generic kernel chain, every hand dense
@@ -677,7 +689,6 @@ int opt_profile_iteration(const ihmr_model* m, int B, int bs_norm, float* params
     prof.tick(9);
     IHMR_CUDA_OK(cudaStreamSynchronize(st));
     for (int i = 0; i < N_KERNEL_CLASSES; ++i) IHMR_CUDA_OK(cudaEventElapsedTime(&ms[i], prof.ev[i], prof.ev[i + 1]));
-    for (auto& e : prof.ev) cudaEventDestroy(e);
     return IHMR_OK;
 }
 

@@ -39,7 +39,12 @@ def frame_metrics(pred_joints_3d: torch.Tensor, gt_joints_3d: torch.Tensor, coll
 class DeviceEvaluator:
     """``update`` after every batch, read the four properties at the end (same names as the reference)."""
 
-    def __init__(self):
+    def __init__(self, data_list=None):
+        """``data_list``: the dataset's per-sample records (``OPTDataset.data_list``).  When given, ``update`` reads
+        ``scale`` and ``hand_type`` of every sample from it as the reference does (evaluator.py:48-58) and frames are
+        de-duplicated by ``img_path`` like ``remove_redunc`` there; without it the caller passes them (defaults:
+        scale 1, every frame interacting)."""
+        self.data_list = data_list
         self.tables: List[np.ndarray] = []
         self.interacting: List[np.ndarray] = []
         self.indices: List[np.ndarray] = []
@@ -50,6 +55,13 @@ class DeviceEvaluator:
     def update(self, data_idxs, model, scale=None, interacting=None):
         """``model``: an ihmr_b200 OptimizeModel after ``optimize()``. ``interacting`` (B,) bool marks the
         frames whose hand_type is 'interacting' (the reference's default, evaluator.py:55-58)."""
+        idx = np.asarray(data_idxs).reshape(-1)
+        if self.data_list is not None:
+            recs = [self.data_list[int(i)] for i in idx]
+            if scale is None:
+                scale = torch.tensor([float(r.get("scale", 1.0)) for r in recs], dtype=torch.float32)
+            if interacting is None:
+                interacting = np.array([r.get("hand_type", "interacting") == "interacting" for r in recs], bool)
         t = frame_metrics(model.pred_joints_3d, model.joints_3d, model.collision_loss_origin_scale, scale)
         self.tables.append(t.cpu().numpy().astype(np.float64))
         B = t.shape[0]
@@ -64,7 +76,11 @@ class DeviceEvaluator:
     def remove_redunc(self):
         """Drop repeated frame ids (the reference pads the dataset and de-duplicates, evaluator.py:137-146)."""
         idx = np.concatenate(self.indices)
-        _, first = np.unique(idx, return_index=True)
+        key = idx
+        if self.data_list is not None:           # the reference keys on img_path_relative (evaluator.py:137-146)
+            names = {}
+            key = np.array([names.setdefault(self.data_list[int(i)]["img_path"], len(names)) for i in idx])
+        _, first = np.unique(key, return_index=True)
         keep = np.sort(first)
         self.tables = [np.concatenate(self.tables)[keep]]
         self.interacting = [np.concatenate(self.interacting)[keep]]

@@ -414,30 +414,37 @@ class OptimizeModel:
         return dict(zip(_lib.KERNEL_CLASSES, [float(x) for x in ms]))
 
     def get_current_errors(self):
-        """optimize_model.py:438-455 (log-only values; plain tensor arithmetic on the exported
-        outputs, not part of the refinement loop)."""
+        """optimize_model.py:438-455: the GT-based log values of __compute_loss (:276-306) plus the two criteria.  Log
+        only — plain tensor arithmetic on the exported outputs, not part of the refinement loop.
+
+        The exported ``pred_joints_3d`` were root aligned in place twice (loss_utils.py:91-104): by the GT wrist
+        weights, then by the prior's (always 1, joint 0), so they are relative to the right wrist whatever the GT
+        says.  The GT-based 3-D value needs the alignment of the first rule only: right wrist present (w > 0.5) ->
+        joint 0, absent (w < 1e-7) -> joint 21, anything between -> not aligned at all."""
         losses, _ = self.value_and_grad(dict(update_params=[], loss_weights=self.default_loss_weights, lr=0.0,
                                              epoch=0, filter_loss=[("joints_3d_loss_p", "+0")],
                                              select_loss="joints_3d_loss_p"))
         l = losses.cpu().numpy()
-        B = float(self.batch_size)
+        n = float(self.bs_norm)
         with torch.no_grad():
-            # the exported joints are root aligned; the 2-D projection needs the right wrist back
             root = self.mano_models["right"](global_orient=self.pred_right_orient.contiguous(),
                                              hand_pose=self.pred_right_pose_params.contiguous(),
                                              betas=self.pred_right_shape_params.contiguous()).joints[:, 0:1]
-            has_r = (self.joints_3d[:, 0, 3] > 0.5).view(-1, 1, 1).float()
-            world = self.pred_joints_3d + root * has_r
+            world = self.pred_joints_3d + root                      # the joints before any alignment
             cam = self.pred_cam_params.reshape(-1, 1, 3)
             j2d = cam[:, :, 0:1] * (world[:, :, :2] + cam[:, :, 1:])
             d2 = (self.joints_2d[:, :, :2] - j2d).abs() * self.joints_2d[:, :, 2:3]
-            gt = self.joints_3d[:, :, :3] - self.joints_3d[:, 0:1, :3] * has_r
-            d3 = (gt - self.pred_joints_3d) ** 2 * self.joints_3d[:, :, 3:4]
+            w0 = self.joints_3d[:, 0, 3].view(-1, 1, 1)
+            has_r, no_r = (w0 > 0.5).float(), (w0 < 1e-7).float()
+
+            def align(j):
+                return j - j[:, 0:1] * has_r - j[:, 21:22] * no_r
+            d3 = (align(self.joints_3d[:, :, :3]) - align(world)) ** 2 * self.joints_3d[:, :, 3:4]
             dt = (self.hand_trans[:, :, :3] - self.pred_hand_trans) ** 2 * self.hand_trans[:, :, 3:4]
         return OrderedDict([
-            ("joints_2d_loss", float(d2.mean().item())),
-            ("joints_3d_loss", float(d3.mean().item()) * 1000),
-            ("hand_trans_loss", float(dt.mean().item()) * 10),
-            ("collision_loss", float(l[3]) * self.bs_norm / B),
-            ("joints_3d_loss_p", float(l[1]) * self.bs_norm / B),
+            ("joints_2d_loss", float(d2.sum().item()) / (n * 84)),
+            ("joints_3d_loss", float(d3.sum().item()) / (n * 126) * 1000),
+            ("hand_trans_loss", float(dt.sum().item()) / (n * 3) * 10),
+            ("collision_loss", float(l[3])),
+            ("joints_3d_loss_p", float(l[1])),
         ])

@@ -254,6 +254,27 @@ def test_value_and_grad_under_another_ray_axis(model_root, oracle_layers, stage_
     assert abs(float(ref_x.collision_loss) - r) > 1e-3 * abs(r)          # the +x convention gives another value
 
 
+def test_current_errors_match_the_reference_log_values(model_root, oracle_layers):
+    """get_current_errors (optimize_model.py:438-455): the GT-based log values, including frames whose GT has no right
+    wrist (aligned to joint 21 first, loss_utils.py:91-99) or a wrist weight between the two thresholds (not aligned)."""
+    from ihmr_b200.optimize_model import OptimizeModel
+    B = 4
+    data = H.make_batch(oracle_layers[0], 0, B, mode="collision")
+    data["joints_3d"] = np.array(data["joints_3d"])
+    data["joints_3d"][1, 0, 3] = 0.0          # no right wrist
+    data["joints_3d"][2, 0, 3] = 0.3          # neither rule applies
+    batch = H.torch_batch(data)
+    hl = H.oracle_loop(oracle_layers, B, 1, 1)
+    hl.set_input(batch); hl.init_optimize(); hl.forward(); hl.compute_loss(hl.strategy[0]["loss_weights"])
+    model = OptimizeModel(H.make_opt(model_root, B))
+    model.set_input(batch); model.init_optimize(); model.forward()
+    got = model.get_current_errors()
+    want = dict(joints_2d_loss=hl.joints_2d_loss, joints_3d_loss=hl.joints_3d_loss, hand_trans_loss=hl.hand_trans_loss)
+    for k, v in want.items():
+        assert abs(got[k] - float(v)) <= 1e-4 * max(abs(float(v)), 1e-6), (k, got[k], float(v))
+    assert list(got) == ["joints_2d_loss", "joints_3d_loss", "hand_trans_loss", "collision_loss", "joints_3d_loss_p"]
+
+
 # ------------------------------------------------------------------------- whole loop
 @pytest.mark.parametrize("fixture", ["loop_b2_short.npz", "loop_collision_short.npz", "loop_cfg1.npz", "loop_mixed6.npz"])
 def test_full_loop_vs_golden(model_root, fixture):

@@ -51,3 +51,29 @@ def test_device_evaluator_end_to_end(model_root, oracle_layers):
     want = MO.summary(MO.frame_table(res["pred_joints_3d"], res["gt_joints_3d"], res["collision_loss_origin_scale"]))
     for k, v in want.items():
         assert abs(getattr(ev, k) - v) <= 1e-5 * max(abs(v), 1e-6), k
+
+
+@pytest.mark.gpu
+def test_device_evaluator_reads_scale_and_hand_type_from_the_data_list(model_root, oracle_layers):
+    """With the dataset's records the device evaluator takes `scale` and `hand_type` per sample as the reference's
+    Evaluator does (evaluator.py:48-58) and de-duplicates by image path."""
+    from ihmr_b200.evaluator import DeviceEvaluator
+    from ihmr_b200.optimize_model import OptimizeModel
+    from ihmr_b200.strategies import opt_default, with_epochs
+    B = 6
+    data = H.make_batch(oracle_layers[0], 0, B)
+    m = OptimizeModel(H.make_opt(model_root, B, save_mid_freq=1, strategy=with_epochs(opt_default, 2)))
+    m.set_input(H.torch_batch(data)); m.init_optimize(); m.optimize(0, 1)
+    scales = [1.0, 0.5, 2.0, 1.5, 1.0, 0.8]
+    types = ["interacting", "right", "interacting", "left", "interacting", "interacting"]
+    data_list = [dict(img_path=f"img_{i % 5}.jpg", scale=scales[i], hand_type=types[i]) for i in range(B)]   # 5 == 0: duplicate
+    ev = DeviceEvaluator(data_list)
+    ev.update(np.arange(B), m)
+    ev.remove_redunc()
+    res = m.get_pred_result()
+    keep = np.arange(5)
+    tab = MO.frame_table(res["pred_joints_3d"][keep], res["gt_joints_3d"][keep], res["collision_loss_origin_scale"][keep],
+                         scale=np.array(scales)[keep])
+    want = MO.summary(tab, interacting=np.array([t == "interacting" for t in types])[keep])
+    for k, v in want.items():
+        assert abs(getattr(ev, k) - v) <= 1e-5 * max(abs(v), 1e-6), k
