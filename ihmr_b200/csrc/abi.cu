@@ -264,6 +264,7 @@ size_t ihmr_mano_workspace_bytes(int n_hands) { return n_hands > 0 ? mano_ws_byt
 int ihmr_mano_forward(const ihmr_model_t* m, int n, const float* global_orient, const float* hand_pose,
                       const float* betas, float* vertices, float* joints, void* workspace,
                       size_t workspace_bytes, ihmr_stream_t stream) {
+    NvtxRange range("ihmr_mano_forward");
     IHMR_CHECK_ARG(m && n >= 0 && global_orient && hand_pose && betas && vertices && workspace);
     if (workspace_bytes < mano_ws_bytes(n)) { set_error("workspace too small: %zu < %zu", workspace_bytes, mano_ws_bytes(n)); return IHMR_E_WORKSPACE; }
     DeviceGuard guard(m->device);
@@ -281,6 +282,7 @@ int ihmr_mano_backward(const ihmr_model_t* m, int n, const float* global_orient,
                        const float* betas, const float* grad_vertices, const float* grad_joints,
                        float* grad_global_orient, float* grad_hand_pose, float* grad_betas,
                        void* workspace, size_t workspace_bytes, ihmr_stream_t stream) {
+    NvtxRange range("ihmr_mano_backward");
     IHMR_CHECK_ARG(m && n >= 0 && global_orient && hand_pose && betas && workspace);
     IHMR_CHECK_ARG(grad_global_orient && grad_hand_pose && grad_betas);
     if (workspace_bytes < mano_ws_bytes(n)) { set_error("workspace too small: %zu < %zu", workspace_bytes, mano_ws_bytes(n)); return IHMR_E_WORKSPACE; }

@@ -1,6 +1,7 @@
 // Shared definitions for the ihmr_b200 kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -21,6 +22,14 @@ constexpr int PD = IHMR_PARAM_DIM;        // 122
 // offsets inside a (B,122) parameter row
 constexpr int P_CAM = 0, P_TRANS = 3, P_POSE = 6, P_SHAPE = 102;
 constexpr int P_R_ORIENT = 6, P_R_POSE = 9, P_L_ORIENT = 54, P_L_POSE = 57, P_R_SHAPE = 102, P_L_SHAPE = 112;
+
+// NVTX range over a host-side entry point (visible in Nsight Systems / Compute timelines; a no-op without a tool attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 void set_error(const char* fmt, ...);
 void count_launch();   // every kernel launch of this library passes through IHMR_LAUNCH_OK

@@ -622,6 +622,7 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
 
 int opt_stage(const ihmr_model* m, int B, int bs_norm, float* params, const ihmr_targets_t* tg,
               const ihmr_stage_t* stg, int save_mid_freq, int optimizer, void* ws, cudaStream_t st) {
+    NvtxRange range("ihmr_opt_stage");
     OptWs w;
     opt_ws_layout(ws, B, &w);
     IHMR_CUDA_OK(cudaMemsetAsync(w.m, 0, (size_t)B * PD * 4, st));
@@ -733,6 +734,7 @@ int opt_criteria(const ihmr_model* m, int B, const float* params, const ihmr_tar
 int opt_final(const ihmr_model* m, int B, const float* params, const ihmr_targets_t* tg, float* right_verts,
               float* left_verts, float* joints_3d, float* collision_loss, float* collision_origin,
               float* j3d_loss_p, void* ws, cudaStream_t st) {
+    NvtxRange range("ihmr_opt_final");
     OptWs w;
     opt_ws_layout(ws, B, &w);
     int rc;

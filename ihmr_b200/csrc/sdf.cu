@@ -1295,6 +1295,7 @@ int launch_sdf_exact(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t 
 
 int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     if (B <= 0) return IHMR_OK;
+    NvtxRange range("ihmr_sdf");
     if (!a.ws) { set_error("sdf: no workspace"); return IHMR_E_INVALID; }
     static unsigned long long configured[3] = {0ull, 0ull, 0ull};
     static int ctas_per_sm[3] = {0, 0, 0};
