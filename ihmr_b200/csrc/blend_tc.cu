@@ -281,8 +281,9 @@ __device__ __forceinline__ uint64_t umma_desc_k16(uint32_t saddr) {
 template <int MODE>
 __global__ void __launch_bounds__(SKT_THREADS, 1)
 k_skin_fwd_tc(int n, const float* __restrict__ off, const float* __restrict__ A, const float* __restrict__ vtemp,
-              const float* __restrict__ W4, float* __restrict__ verts) {
+              const float* __restrict__ W4, float* __restrict__ verts, float* __restrict__ bbox) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ int s_box[SKT_HANDS][6];                           // MODE 0: boxes of the group's hands (for the penetration op)
     unsigned char* w_hi = smem;                                   // [7][128 x 16]
     unsigned char* w_lo = w_hi + SKT_TILES * SKT_W_TILE;
     unsigned char* b_hi = w_lo + SKT_TILES * SKT_W_TILE;          // [192 x 16]
@@ -345,6 +346,8 @@ k_skin_fwd_tc(int n, const float* __restrict__ off, const float* __restrict__ A,
             const uint32_t o = (row >> 3) * SKT_SBO + kc * TC_LBO + (row & 7) * 16;
             split_store(v, reinterpret_cast<float4*>(b_hi + o), reinterpret_cast<float4*>(b_lo + o));
         }
+        if (MODE == 0 && bbox && tid < SKT_HANDS * 6) box_slot_init(s_box[tid / 6], tid % 6);
+        BoxAcc box[4];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid == 0) { issue_tile(0); issue_tile(1); }
@@ -389,10 +392,14 @@ k_skin_fwd_tc(int n, const float* __restrict__ off, const float* __restrict__ A,
                 if (vok && hh < nh) {
                     if (MODE == 0) {
                         float* o = verts + ((size_t)(h0 + hh) * NV + v) * 3;
+                        float x[3];
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            o[c] = __uint_as_float(r[c * 4 + 0]) * vp[q][0] + __uint_as_float(r[c * 4 + 1]) * vp[q][1] +
+                        for (int c = 0; c < 3; ++c) {
+                            x[c] = __uint_as_float(r[c * 4 + 0]) * vp[q][0] + __uint_as_float(r[c * 4 + 1]) * vp[q][1] +
                                    __uint_as_float(r[c * 4 + 2]) * vp[q][2] + __uint_as_float(r[c * 4 + 3]);
+                            o[c] = x[c];
+                        }
+                        box[q].add(x[0], x[1], x[2]);
                     } else {
                         float* o = verts + (size_t)(h0 + hh) * LDN + v * 3;
 #pragma unroll
@@ -407,6 +414,14 @@ k_skin_fwd_tc(int n, const float* __restrict__ off, const float* __restrict__ A,
             if (tid == 0 && t + 2 < SKT_TILES) issue_tile(t + 2);
         }
         // all seven commits were awaited: the B operand may be restaged
+        if (MODE == 0 && bbox) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) box[q].commit(s_box[hsub * 4 + q]);
+            __syncthreads();
+            if (tid < SKT_HANDS * 6 && tid / 6 < nh) bbox[(size_t)(h0 + tid / 6) * 6 + tid % 6] = ordered_float(s_box[tid / 6][tid % 6]);
+            // (the slots are re-initialised before the next group's first barrier, after this read: the restaging loop
+            //  above runs first and thread tid re-initialises the very slot it has just read)
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -414,13 +429,13 @@ k_skin_fwd_tc(int n, const float* __restrict__ off, const float* __restrict__ A,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(512) : "memory");
 }
 
-int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st) {
+int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st, float* bbox) {
     if (n <= 0) return IHMR_OK;
     const size_t smem = 2 * (size_t)SKT_TILES * SKT_W_TILE + 2 * SKT_B_BYTES;
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_skin_fwd_tc<0>, smem, configured)) return rc;
     const int ngroups = (n + SKT_HANDS - 1) / SKT_HANDS;
-    k_skin_fwd_tc<0><<<min(ngroups, m->num_sms), SKT_THREADS, smem, st>>>(n, off, A, m->vtemp, m->W4, verts);
+    k_skin_fwd_tc<0><<<min(ngroups, m->num_sms), SKT_THREADS, smem, st>>>(n, off, A, m->vtemp, m->W4, verts, bbox);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }

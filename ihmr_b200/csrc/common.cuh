@@ -31,6 +31,48 @@ struct NvtxRange {
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
+#ifdef __CUDACC__
+// floats <-> integers with the same ordering (an involution on the bit pattern)
+__device__ __forceinline__ int float_ordered(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// Bounding box of a hand's vertices, emitted by the kernels that write them (the penetration op needs it per frame;
+// min / max are exact and order independent, so the box is bitwise the one a scan of the stored vertices gives).
+// `slot`: six shared-memory ints (ordered lo xyz, hi xyz), initialised with box_slot_init and complete after a barrier.
+struct BoxAcc {
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    __device__ __forceinline__ void add(float x, float y, float z) {
+        lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+        hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+    }
+    // whole warp: one REDUX per value, lane 0 merges into the slot
+    __device__ __forceinline__ void commit(int* slot) const {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int l = __reduce_min_sync(0xffffffffu, float_ordered(lo[c]));
+            const int h = __reduce_max_sync(0xffffffffu, float_ordered(hi[c]));
+            if ((threadIdx.x & 31) == 0) { atomicMin(slot + c, l); atomicMax(slot + 3 + c, h); }
+        }
+    }
+    // whole warp: lane 0 stores the warp's box (six ordered ints) into its own row; merge_rows combines the rows
+    __device__ __forceinline__ void store_row(int* row) const {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int l = __reduce_min_sync(0xffffffffu, float_ordered(lo[c]));
+            const int h = __reduce_max_sync(0xffffffffu, float_ordered(hi[c]));
+            if ((threadIdx.x & 31) == 0) { row[c] = l; row[3 + c] = h; }
+        }
+    }
+};
+// entry k (0..5) of the box over `nrows` per-warp rows of six ordered ints
+__device__ __forceinline__ float box_merge_rows(const int* rows, int nrows, int k) {
+    int v = rows[k];
+    for (int w = 1; w < nrows; ++w) v = (k < 3) ? min(v, rows[w * 6 + k]) : max(v, rows[w * 6 + k]);
+    return ordered_float(v);
+}
+__device__ __forceinline__ void box_slot_init(int* slot, int k) { slot[k] = (k < 3) ? 0x7fffffff : (int)0x80000000; }
+#endif
+
 void set_error(const char* fmt, ...);
 void count_launch();   // every kernel launch of this library passes through IHMR_LAUNCH_OK
 

@@ -39,7 +39,7 @@ int launch_pose_prep(const ihmr_model* m, int n, HandSrc src, float* X, float* A
                      cudaStream_t st);
 int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cudaStream_t st);
 int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts,
-                    cudaStream_t st);
+                    cudaStream_t st, float* bbox = nullptr);
 // Hands whose vertex gradient is identically zero (flagged by the penetration kernels) carry only their five
 // fingertip gradients: the backward kernels take a short path for them and the blend contraction skips them.
 struct SparseGrad {
@@ -56,16 +56,20 @@ int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A
 int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp = SparseGrad());
 // orientation-only stages (fused layout only): cache L = R0^T (x - J0), then x = R0 L + J0 and its backward
 int launch_rigid_prep(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
-int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
+int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st,
+                     float* bbox = nullptr);
 int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips, const float* gjoints, const float* Lv,
                      const float* Lj, float* params_grad, cudaStream_t st, SparseGrad sp = SparseGrad());
 // shape-only stages (fused layout only): cache (T_v | T_v c_v) per vertex, then the affine forward / backward in beta
 int launch_shape_prep(const ihmr_model* m, int n, HandSrc src, const float* off, const float* A, float* cache, cudaStream_t st);
-int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st);
+int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st,
+                     float* bbox = nullptr);
 int launch_shape_bwd(const ihmr_model* m, int n, const float* cache, const float* gverts, const float* gtips, float* dA,
                      float* dX, cudaStream_t st, SparseGrad sp = SparseGrad());
 // skinning forward with the blend T = W . A^T on tcgen05 (blend_tc.cu)
-int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st);
+// bbox (n,6) or null: lo xyz, hi xyz of every hand's vertices (for the penetration op)
+int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st,
+                       float* bbox = nullptr);
 // C[M,Nc] = A[M,K] . B[Nc,K]^T on tcgen05 with 3xTF32 splitting (blend_tc.cu)
 // rows / nrows (device, optional): row r of the product uses row rows[r] of A and of C, for r < *nrows <= M
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
@@ -83,6 +87,8 @@ int launch_pose_bwd(const ihmr_model* m, int n, HandSrc src, const float* dA, co
 // their sum over the left hand (= d/d shift, world frame) goes to gshift (B,3).
 struct SdfArgs {
     const float* verts = nullptr;
+    const float* bbox = nullptr;       // (B,2,6) or null: lo xyz, hi xyz of the STORED vertices of every hand, as left by
+                                       // the kernel that wrote them; null = k_sdf_prep scans the vertices
     const float* joints = nullptr;     // (B,2,16,3) or null
     const float* params = nullptr;     // (B,122) or null
     const float* hand_type = nullptr;  // (B,2) or null: loss/grad masked unless both hands present

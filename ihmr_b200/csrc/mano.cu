@@ -635,26 +635,59 @@ __device__ __forceinline__ void root_rotation(const HandSrc& src, int h, float* 
 
 constexpr int RG_THREADS = 256;
 
-// mode 0: L = R0^T (x - J0) from the generic forward's verts/joints; mode 1: x = R0 L + J0
-template <int MODE>
+// L = R0^T (x - J0) from the generic forward's verts/joints (first iteration of an orientation-only stage)
 __global__ void __launch_bounds__(RG_THREADS)
-k_rigid_xform(int n, HandSrc src, float* __restrict__ verts, float* __restrict__ joints, float* __restrict__ Lv,
-              float* __restrict__ Lj) {
+k_rigid_prep(int n, HandSrc src, const float* __restrict__ verts, const float* __restrict__ joints, float* __restrict__ Lv,
+             float* __restrict__ Lj) {
     const int h = blockIdx.x, tid = threadIdx.x;
     float r[3], theta, R[9];
     root_rotation<true>(src, h, r, theta, R);
     const float J0[3] = {joints[(size_t)h * 48], joints[(size_t)h * 48 + 1], joints[(size_t)h * 48 + 2]};
     for (int i = tid; i < NV + NJ; i += RG_THREADS) {
-        float* x = i < NV ? verts + ((size_t)h * NV + i) * 3 : joints + ((size_t)h * NJ + (i - NV)) * 3;
+        const float* x = i < NV ? verts + ((size_t)h * NV + i) * 3 : joints + ((size_t)h * NJ + (i - NV)) * 3;
         float* l = i < NV ? Lv + (size_t)h * LDN + i * 3 : Lj + (size_t)h * 192 + (i - NV) * 3;
-        if (MODE == 0) {
-            const float d[3] = {x[0] - J0[0], x[1] - J0[1], x[2] - J0[2]};
+        const float d[3] = {x[0] - J0[0], x[1] - J0[1], x[2] - J0[2]};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) l[c] = R[0 * 3 + c] * d[0] + R[1 * 3 + c] * d[1] + R[2 * 3 + c] * d[2];
-        } else if (i != NV) {                      // the wrist itself (joint 0) never moves
-            const float a[3] = {l[0], l[1], l[2]};
+        for (int c = 0; c < 3; ++c) l[c] = R[0 * 3 + c] * d[0] + R[1 * 3 + c] * d[1] + R[2 * 3 + c] * d[2];
+    }
+}
+
+// x = R0 L + J0, one warp per hand (no block barrier: the hand's bounding box for the penetration op is a warp
+// reduction).  The wrist itself (joint 0) never moves.
+constexpr int RGF_WARPS = 8;
+__global__ void __launch_bounds__(RGF_WARPS * 32)
+k_rigid_fwd(int n, HandSrc src, float* __restrict__ verts, float* __restrict__ joints, const float* __restrict__ Lv,
+            const float* __restrict__ Lj, float* __restrict__ bbox) {
+    const int lane = threadIdx.x & 31, h = blockIdx.x * RGF_WARPS + (threadIdx.x >> 5);
+    if (h >= n) return;
+    float r[3], theta, R[9];
+    root_rotation<true>(src, h, r, theta, R);
+    const float J0[3] = {joints[(size_t)h * 48], joints[(size_t)h * 48 + 1], joints[(size_t)h * 48 + 2]};
+    BoxAcc box;
+    const float* lv = Lv + (size_t)h * LDN;
+    float* xv = verts + (size_t)h * NV * 3;
+#pragma unroll 5
+    for (int i = lane; i < NV; i += 32) {
+        const float a[3] = {lv[i * 3], lv[i * 3 + 1], lv[i * 3 + 2]};
+        float y[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) x[c] = R[c * 3 + 0] * a[0] + R[c * 3 + 1] * a[1] + R[c * 3 + 2] * a[2] + J0[c];
+        for (int c = 0; c < 3; ++c) { y[c] = R[c * 3 + 0] * a[0] + R[c * 3 + 1] * a[1] + R[c * 3 + 2] * a[2] + J0[c]; xv[i * 3 + c] = y[c]; }
+        box.add(y[0], y[1], y[2]);
+    }
+    if (lane >= 1 && lane < NJ) {
+        const float* l = Lj + (size_t)h * 192 + lane * 3;
+        float* x = joints + ((size_t)h * NJ + lane) * 3;
+        const float a[3] = {l[0], l[1], l[2]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = R[c * 3 + 0] * a[0] + R[c * 3 + 1] * a[1] + R[c * 3 + 2] * a[2] + J0[c];
+    }
+    if (bbox) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int l = __reduce_min_sync(0xffffffffu, float_ordered(box.lo[c]));
+            const int hgh = __reduce_max_sync(0xffffffffu, float_ordered(box.hi[c]));
+            if (lane == c) bbox[(size_t)h * 6 + c] = ordered_float(l);
+            if (lane == 3 + c) bbox[(size_t)h * 6 + 3 + c] = ordered_float(hgh);
         }
     }
 }
@@ -727,14 +760,14 @@ k_rigid_bwd(int n, HandSrc src, const float* __restrict__ gverts, const float* _
 
 int launch_rigid_prep(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st) {
     if (n <= 0) return IHMR_OK;
-    k_rigid_xform<0><<<n, RG_THREADS, 0, st>>>(n, src, verts, joints, Lv, Lj);
+    k_rigid_prep<<<n, RG_THREADS, 0, st>>>(n, src, verts, joints, Lv, Lj);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
 
-int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st) {
+int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st, float* bbox) {
     if (n <= 0) return IHMR_OK;
-    k_rigid_xform<1><<<n, RG_THREADS, 0, st>>>(n, src, verts, joints, Lv, Lj);
+    k_rigid_fwd<<<(n + RGF_WARPS - 1) / RGF_WARPS, RGF_WARPS * 32, 0, st>>>(n, src, verts, joints, Lv, Lj, bbox);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
@@ -874,8 +907,9 @@ __device__ __forceinline__ void shape_wait(unsigned long long* bar, uint32_t par
 
 __global__ void __launch_bounds__(SH_THREADS, 1)
 k_shape_fwd(int n, HandSrc src, const float* __restrict__ A, const float* __restrict__ W4,
-            const float* __restrict__ Sv, const float4* __restrict__ cache, float* __restrict__ verts) {
+            const float* __restrict__ Sv, const float4* __restrict__ cache, float* __restrict__ verts, float* __restrict__ bbox) {
     extern __shared__ float4 smem4[];
+    __shared__ int s_box[2][SH_THREADS / 32][6];                  // per-warp boxes of the current hand, two buffers
     float4* ring = smem4;                                                             // [SHF_STAGES][3 * NV]
     float4 (*sT)[NJ] = reinterpret_cast<float4 (*)[NJ]>(ring + SHF_STAGES * 3 * NV);  // [SHF_HPC][16] translation columns
     float (*sBeta)[12] = reinterpret_cast<float (*)[12]>(sT + SHF_HPC);               // [SHF_HPC][12]
@@ -921,6 +955,7 @@ k_shape_fwd(int n, HandSrc src, const float* __restrict__ A, const float* __rest
         const float4 b0 = b4[0], b1 = b4[1], b2 = b4[2];
         const float beta[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
         float t[SH_ITEMS_F][3];
+        BoxAcc box;
 #pragma unroll
         for (int sl = 0; sl < SH_ITEMS_F; ++sl) { t[sl][0] = 0.f; t[sl][1] = 0.f; t[sl][2] = 0.f; }
 #pragma unroll
@@ -940,15 +975,21 @@ k_shape_fwd(int n, HandSrc src, const float* __restrict__ A, const float* __rest
                 u[a] = sb;
             }
             if (tid + sl * SH_THREADS < NV) {
+                float x[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float4 row = rows[r * NV + vv[sl]];
-                    verts[(h * NV + vv[sl]) * 3 + r] = (row.w + t[sl][r]) + (row.x * u[0] + row.y * u[1] + row.z * u[2]);
+                    x[r] = (row.w + t[sl][r]) + (row.x * u[0] + row.y * u[1] + row.z * u[2]);
+                    verts[(h * NV + vv[sl]) * 3 + r] = x[r];
                 }
+                box.add(x[0], x[1], x[2]);
             }
         }
-        __syncthreads();                                      // every thread is done with this stage
+        if (bbox) box.store_row(s_box[hh & 1][tid >> 5]);
+        __syncthreads();                                      // every thread is done with this stage (and with the hand's box)
         if (tid == 0 && hh + SHF_STAGES < nh) shape_issue(cache, h + SHF_STAGES, ring + st * 3 * NV, &bars[st]);
+        // (the other buffer takes the next hand's rows; this one is rewritten after the next barrier)
+        if (bbox && tid >= 32 && tid < 38) bbox[h * 6 + (tid - 32)] = box_merge_rows(&s_box[hh & 1][0][0], SH_THREADS / 32, tid - 32);
     }
 }
 
@@ -1181,12 +1222,13 @@ int launch_shape_prep(const ihmr_model* m, int n, HandSrc src, const float* off,
 
 constexpr size_t SHAPE_FWD_SMEM = sizeof(float4) * (SHF_STAGES * 3 * NV + SHF_HPC * NJ) + sizeof(float) * SHF_HPC * 12;
 
-int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st) {
+int launch_shape_fwd(const ihmr_model* m, int n, HandSrc src, const float* A, const float* cache, float* verts, cudaStream_t st,
+                     float* bbox) {
     if (n <= 0) return IHMR_OK;
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_shape_fwd, SHAPE_FWD_SMEM, configured)) return rc;
     k_shape_fwd<<<(n + SHF_HPC - 1) / SHF_HPC, SH_THREADS, SHAPE_FWD_SMEM, st>>>(n, src, A, m->W4, m->Sv,
-                                                                               reinterpret_cast<const float4*>(cache), verts);
+                                                                               reinterpret_cast<const float4*>(cache), verts, bbox);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
@@ -1263,9 +1305,9 @@ int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const f
     return IHMR_OK;
 }
 
-int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st) {
+int launch_skin_fwd(const ihmr_model* m, int n, const float* off, const float* A, float* verts, cudaStream_t st, float* bbox) {
     if (n <= 0) return IHMR_OK;
-    return launch_skin_fwd_tc(m, n, off, A, verts, st);      // the blend T = W . A^T runs on tcgen05 (blend_tc.cu)
+    return launch_skin_fwd_tc(m, n, off, A, verts, st, bbox);      // the blend T = W . A^T runs on tcgen05 (blend_tc.cu)
 }
 
 int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A, const float* gverts,

@@ -416,6 +416,7 @@ struct OptWs {
     uint16_t* sdf_hints;      // nearest-face seeds the penetration kernel carries from one iteration to the next
     uint32_t* sdf_pcache;     // static-grid caches of the penetration kernel (stages that move only hand_trans)
     float* sdf_phic;
+    float* bbox;              // (N, 6) box of every hand's stored vertices, left by the kernel that wrote them
     uint8_t* gzero;           // (N) hands whose collision gradient is identically zero this iteration
     int* dense_list;          // (N) the other hands, [N] = their count
 };
@@ -457,6 +458,7 @@ static size_t opt_ws_layout(void* base, int B, OptWs* out) {
     w.sdf_hints = (uint16_t*)take(sdf_hint_bytes(B));
     w.sdf_pcache = (uint32_t*)take(sdf_pcache_bytes(B));
     w.sdf_phic = (float*)take(sdf_phic_bytes(B));
+    w.bbox = (float*)take((size_t)n * 6 * 4);
     w.gzero = (uint8_t*)take((size_t)n);
     w.dense_list = (int*)take((size_t)(n + 1) * 4);
     if (out) *out = w;
@@ -490,7 +492,7 @@ static int forward_all(const ihmr_model* m, int B, const float* params, OptWs& w
     IHMR_TICK(prof, 1);
     if ((rc = launch_blend_fwd(m, 2 * B, w.mano.X, w.mano.off, st))) return rc;
     IHMR_TICK(prof, 2);
-    if ((rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st))) return rc;
+    if ((rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st, w.bbox))) return rc;
     IHMR_TICK(prof, 3);
     return IHMR_OK;
 }
@@ -573,16 +575,17 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     IHMR_TICK(prof, 1);
     if (plan.blend_fwd && (rc = launch_blend_fwd(m, 2 * B, w.mano.X, w.mano.off, st))) return rc;
     IHMR_TICK(prof, 2);
-    if (plan.mano_fwd && plan.shape != 2 && (rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st))) return rc;
+    if (plan.mano_fwd && plan.shape != 2 && (rc = launch_skin_fwd(m, 2 * B, w.mano.off, w.mano.A, w.verts, st, w.bbox))) return rc;
     // shape-only stage: pose_prep above refreshed the joints and the translation columns of A
     if (plan.shape == 1 && (rc = launch_shape_prep(m, 2 * B, src, w.mano.off, w.mano.A, w.shape_cache, st))) return rc;
-    if (plan.shape == 2 && (rc = launch_shape_fwd(m, 2 * B, src, w.mano.A, w.shape_cache, w.verts, st))) return rc;
+    if (plan.shape == 2 && (rc = launch_shape_fwd(m, 2 * B, src, w.mano.A, w.shape_cache, w.verts, st, w.bbox))) return rc;
     // orientation-only stage: the root-local geometry lives in the (otherwise idle) gposed / dA buffers
     if (plan.rigid == 1 && (rc = launch_rigid_prep(2 * B, src, w.verts, w.joints, w.mano.gposed, w.mano.dA, st))) return rc;
-    if (plan.rigid == 2 && (rc = launch_rigid_fwd(2 * B, src, w.verts, w.joints, w.mano.gposed, w.mano.dA, st))) return rc;
+    if (plan.rigid == 2 && (rc = launch_rigid_fwd(2 * B, src, w.verts, w.joints, w.mano.gposed, w.mano.dA, st, w.bbox))) return rc;
     IHMR_TICK(prof, 3);
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
+    sa.bbox = w.bbox;         // every writer of w.verts leaves the hands' boxes there (iterations that keep the vertices keep them)
     sa.ws = w.sdf_ws; sa.hints = carry_hints ? w.sdf_hints : nullptr;
     if (carry_hints && plan.static_right) { sa.static_grid_mask = 1; sa.pcache = w.sdf_pcache; sa.phic = w.sdf_phic; } sa.gverts = (plan.mano_bwd || plan.rigid) ? w.gverts : nullptr; sa.gshift = w.gshift;
     // generic backward chain: hands without collision gradient take the fingertip-only path (flags from the sdf kernels,
@@ -719,7 +722,7 @@ int opt_criteria(const ihmr_model* m, int B, const float* params, const ihmr_tar
     if ((rc = forward_all(m, B, params, w, st))) return rc;
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
-    sa.losses = w.col_loss; sa.ws = w.sdf_ws;
+    sa.losses = w.col_loss; sa.ws = w.sdf_ws; sa.bbox = w.bbox;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
     ihmr_stage_t wts{};
     wts.w_joints_2d = w_joints_2d; wts.w_joints_3d = w_joints_3d;
@@ -742,7 +745,7 @@ int opt_final(const ihmr_model* m, int B, const float* params, const ihmr_target
     SdfArgs sa;
     sa.verts = w.verts; sa.joints = w.joints; sa.params = params; sa.hand_type = tg->hand_type_array;
     sa.losses = collision_loss ? collision_loss : w.col_loss;
-    sa.origin = collision_origin; sa.ws = w.sdf_ws;
+    sa.origin = collision_origin; sa.ws = w.sdf_ws; sa.bbox = w.bbox;
     if ((rc = launch_sdf(m, B, sa, st))) return rc;
     ihmr_stage_t dflt{};   // default_loss_weights (optimize_model.py:84-92)
     dflt.w_joints_2d = 10.f; dflt.w_joints_3d = 1000.f; dflt.w_trans = 100.f; dflt.w_shape_reg = 0.1f;

@@ -199,9 +199,7 @@ __device__ __forceinline__ void from_ray_frame(float* v, int axis) {
     if (axis == 1) { v[0] = a2; v[1] = a0; v[2] = a1; } else { v[0] = a1; v[1] = a2; v[2] = a0; }
 }
 
-// floats <-> integers with the same ordering (an involution on the bit pattern)
-__device__ __forceinline__ int float_ordered(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
-__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+// (float_ordered / ordered_float: common.cuh)
 
 // ---- block primitives ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -368,8 +366,17 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) k_sdf_prep(int B, SdfArgs a, 
         }
         float mask = 1.0f;
         if (a.hand_type) mask = (a.hand_type[b * 2] + a.hand_type[b * 2 + 1] > 1.5f) ? 1.0f : 0.0f;
-        const float* V = a.verts + (size_t)b * (2 * NV * 3);
         float lo[2][3], hi[2][3];
+        if (a.bbox) {                        // the kernels that wrote the vertices left their boxes (stored frame)
+#pragma unroll
+            for (int hnd = 0; hnd < 2; ++hnd)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    lo[hnd][c] = a.bbox[((size_t)b * 2 + hnd) * 6 + c];
+                    hi[hnd][c] = a.bbox[((size_t)b * 2 + hnd) * 6 + 3 + c];
+                }
+        } else {
+        const float* V = a.verts + (size_t)b * (2 * NV * 3);
 #pragma unroll
         for (int hnd = 0; hnd < 2; ++hnd)
 #pragma unroll
@@ -391,6 +398,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) k_sdf_prep(int B, SdfArgs a, 
                 lo[hnd][c] = ordered_float(__reduce_min_sync(0xffffffffu, float_ordered(lo[hnd][c])));
                 hi[hnd][c] = ordered_float(__reduce_max_sync(0xffffffffu, float_ordered(hi[hnd][c])));
             }
+        }
         if (xform) {
             // world frame of the stored (mirrored) left hand: x -> -x + shift, y,z -> + shift.  Rounding is
             // monotone, so the box of the mapped vertices is the mapped box.

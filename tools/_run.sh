@@ -1,2 +1,8 @@
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -15
-VARIANTS="" tools/sdf_variants.sh 65536
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -4
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/b_l.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/b_l.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'])
+for s in d['step_roofline']['kernel_ms_per_stage']: print({k:round(v,3) for k,v in s.items()}, round(sum(s.values()),2))
+PY
