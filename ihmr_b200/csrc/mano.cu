@@ -692,66 +692,59 @@ k_rigid_fwd(int n, HandSrc src, float* __restrict__ verts, float* __restrict__ j
     }
 }
 
-// d loss / d orient = rodrigues_bwd( sum_points g (x) L ), added to the orient slots of the gradient rows
-__global__ void __launch_bounds__(RG_THREADS)
+// d loss / d orient = rodrigues_bwd( sum_points g (x) L ), added to the orient slots of the gradient rows.
+// One warp per hand: a hand without collision gradient (two thirds of them) has only its five fingertip vertices and
+// the joints to visit, a single trip; the 3x3 sum is a fixed-order lane sum + butterfly, no block barrier.
+__global__ void __launch_bounds__(RGF_WARPS * 32)
 k_rigid_bwd(int n, HandSrc src, const float* __restrict__ gverts, const float* __restrict__ gtips,
             const float* __restrict__ gjoints, const float* __restrict__ Lv, const float* __restrict__ Lj,
             float* __restrict__ params_grad, const uint8_t* __restrict__ gzero) {
-    __shared__ float red[9][RG_THREADS / 32];
-    const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, h = blockIdx.x * RGF_WARPS + (threadIdx.x >> 5);
+    if (h >= n) return;
     float M[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) M[i] = 0.f;
-    // a hand without collision gradient: only the five fingertip vertices and the joints carry gradient
-    const bool sparse = gzero && gzero[h];
-    const int tips[5] = {744, 320, 443, 554, 671};
-    const int nitems = sparse ? 5 + NJ : NV + NJ;
-    for (int it = tid; it < nitems; it += RG_THREADS) {
-        const int i = sparse ? (it < 5 ? tips[it] : NV + it - 5) : it;
-        float g[3];
-        const float* l;
-        if (i < NV) {
-            g[0] = 0.f; g[1] = 0.f; g[2] = 0.f;
-            if (!sparse) {
-                const float* gp = gverts + ((size_t)h * NV + i) * 3;
-                g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
-            }
-            const int tip = (i == 744) ? 0 : (i == 320) ? 1 : (i == 443) ? 2 : (i == 554) ? 3 : (i == 671) ? 4 : -1;
-            if (tip >= 0) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) g[c] += gtips[((size_t)h * 5 + tip) * 3 + c];
-            }
-            l = Lv + (size_t)h * LDN + i * 3;
-        } else {
-            const float* gp = gjoints + ((size_t)h * NJ + (i - NV)) * 3;
-            g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
-            l = Lj + (size_t)h * 192 + (i - NV) * 3;
-        }
+    auto accumulate = [&](const float* g, const float* l) {
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int c = 0; c < 3; ++c) M[a * 3 + c] += g[a] * l[c];
+    };
+    const bool sparse = gzero && gzero[h];
+    const float* lv = Lv + (size_t)h * LDN;
+    if (!sparse) {
+        const float* gv = gverts + (size_t)h * NV * 3;
+#pragma unroll 5
+        for (int i = lane; i < NV; i += 32) {
+            const float g[3] = {gv[i * 3], gv[i * 3 + 1], gv[i * 3 + 2]};
+            const float l[3] = {lv[i * 3], lv[i * 3 + 1], lv[i * 3 + 2]};
+            accumulate(g, l);
+        }
+    }
+    if (lane < 5) {                     // the fingertip joints' gradients arrive on their vertices
+        const int tips[5] = {744, 320, 443, 554, 671};
+        const int i = tips[lane];
+        const float* gp = gtips + ((size_t)h * 5 + lane) * 3;
+        const float g[3] = {gp[0], gp[1], gp[2]};
+        const float l[3] = {lv[i * 3], lv[i * 3 + 1], lv[i * 3 + 2]};
+        accumulate(g, l);
+    } else if (lane >= 8 && lane < 8 + NJ) {
+        const int j = lane - 8;
+        const float* gp = gjoints + ((size_t)h * NJ + j) * 3;
+        const float* lp = Lj + (size_t)h * 192 + j * 3;
+        const float g[3] = {gp[0], gp[1], gp[2]};
+        const float l[3] = {lp[0], lp[1], lp[2]};
+        accumulate(g, l);
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        float v = M[i];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[i][warp] = v;
+        for (int o = 16; o >= 1; o >>= 1) M[i] += __shfl_xor_sync(0xffffffffu, M[i], o);
     }
-    __syncthreads();
-    if (tid == 0) {
-        float dR[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < RG_THREADS / 32; ++w) v += red[i][w];
-            dR[i] = v;
-        }
+    if (lane == 0) {
         float r[3], theta, R[9], dr[3];
         root_rotation<true>(src, h, r, theta, R);
-        rodrigues_bwd(r, theta, dR, dr);
+        rodrigues_bwd(r, theta, M, dr);
         if (h & 1) { dr[1] = -dr[1]; dr[2] = -dr[2]; }
         float* gr = params_grad + (size_t)(h >> 1) * PD + P_POSE + 48 * (h & 1);
         gr[0] += dr[0]; gr[1] += dr[1]; gr[2] += dr[2];
@@ -775,7 +768,7 @@ int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv,
 int launch_rigid_bwd(int n, HandSrc src, const float* gverts, const float* gtips, const float* gjoints, const float* Lv,
                      const float* Lj, float* params_grad, cudaStream_t st, SparseGrad sp) {
     if (n <= 0) return IHMR_OK;
-    k_rigid_bwd<<<n, RG_THREADS, 0, st>>>(n, src, gverts, gtips, gjoints, Lv, Lj, params_grad, sp.gzero);
+    k_rigid_bwd<<<(n + RGF_WARPS - 1) / RGF_WARPS, RGF_WARPS * 32, 0, st>>>(n, src, gverts, gtips, gjoints, Lv, Lj, params_grad, sp.gzero);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
