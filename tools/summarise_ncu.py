@@ -81,7 +81,7 @@ for s, launches in enumerate(stages):
         out_rows.append(row)
         if s == 2 or n not in traffic:
             traffic[n] = {"dram_bytes_per_unit": row["dram_bytes_per_unit"], "unit": row["unit"], "stage": s}
-        if n == "k_sdf_dir" and s == 2:
+        if n.startswith("k_sdf_dir") and s == 2:
             issue["sdf"] = {"kernel": "k_sdf_dir (steady state, stage 2)", "issue_active_pct": row["issue_active_pct"],
                             "ipc_per_sm": row["ipc_per_sm"], "ipc_peak": 4.0, "lanes_per_inst": row["lanes_per_inst"],
                             "dram_pct": row["dram_pct"], "warps_active_pct": row["warps_active_pct"],
@@ -93,14 +93,17 @@ with open(prefix + "_ncu_summary.csv", "w") as fh:
     for r in out_rows:
         w.writerow({k: (f"{v:.4g}" if isinstance(v, float) else v) for k, v in r.items()})
 # bench.py looks the dominant kernel class up by its slot name
-alias = {"sdf": ["k_sdf_dir", "k_sdf_prep"], "skin_bwd": ["k_skin_bwd", "k_skin_bwd_tips"], "skin_fwd": ["k_skin_fwd_tc<0>"],
+alias = {"sdf": ["k_sdf_dir", "k_sdf_prep"], "skin_bwd": ["k_skin_bwd", "k_skin_bwd_tips"], "skin_fwd": ["k_skin_fwd_tc"],
          "blend_fwd": ["k_gemm_tf32x3<256>"], "blend_bwd": ["k_gemm_tf32x3<160>"]}
 kern = {}
 for slot, names in alias.items():
-    tot = [traffic[n]["dram_bytes_per_unit"] for n in names if n in traffic and traffic[n]["dram_bytes_per_unit"] is not None]
-    if tot:
-        per_hand = sum(t / (2 if traffic[n]["unit"] == "frame" else 1) for t, n in zip(tot, [n for n in names if n in traffic]))
-        kern[slot] = {"dram_bytes_per_unit": per_hand, "unit": "hand (half frame)" if slot == "sdf" else "hand"}
+    # (template arguments vary between builds: match the kernel name by prefix, the stage-2 instance wins)
+    found = [next((k for k in traffic if k.startswith(nm) and traffic[k]["stage"] == 2), next((k for k in traffic if k.startswith(nm)), None))
+             for nm in names]
+    found = [k for k in found if k is not None and traffic[k]["dram_bytes_per_unit"] is not None]
+    if found:
+        per_hand = sum(traffic[k]["dram_bytes_per_unit"] / (2 if traffic[k]["unit"] == "frame" else 1) for k in found)
+        kern[slot] = {"dram_bytes_per_unit": per_hand, "unit": "hand (half frame)" if slot == "sdf" else "hand", "kernels": found}
 json.dump({"source": f"{src.split('/')[-1]}: ncu (SpeedOfLight / MemoryWorkloadAnalysis sections), {frames} frames, steady-state iteration of "
                      "stage 2 (dram__bytes.sum over the launch); per launch unit of bench.py (hand = half a frame)",
            "kernels": kern, "all": traffic}, open(prefix + "_traffic.json", "w"), indent=1)
