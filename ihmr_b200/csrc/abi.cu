@@ -190,6 +190,9 @@ int ihmr_model_create(const float* v_template, const float* shapedirs, const flo
         }
     memcpy(hm.data() + 3, hands_mean, 45 * sizeof(float));
     std::vector<float> DT = transpose_D(D);
+    std::vector<float> DTq(gemm_presplit_floats(LDN, KP)), Dq(gemm_presplit_floats(KP, LDN));
+    gemm_presplit_b(DT.data(), LDN, KP, KP, DTq.data());
+    gemm_presplit_b(D.data(), KP, LDN, LDN, Dq.data());
     std::vector<float> Jreg(J_regressor, J_regressor + NJ * NV);
     std::vector<uint16_t> fr(NF * 4, 0), fl(NF * 4, 0);
     for (int f = 0; f < NF; ++f)
@@ -198,7 +201,8 @@ int ihmr_model_create(const float* v_template, const float* shapedirs, const flo
             fl[f * 4 + c] = (uint16_t)faces_left[f * 3 + c];
         }
     int rc;
-    if ((rc = upload(&m->D, D)) || (rc = upload(&m->DT, DT)) || (rc = upload(&m->vtemp, vt)) ||
+    if ((rc = upload(&m->D, D)) || (rc = upload(&m->DT, DT)) || (rc = upload(&m->DTq, DTq)) || (rc = upload(&m->Dq, Dq)) ||
+        (rc = upload(&m->vtemp, vt)) ||
         (rc = upload(&m->Jt, Jt)) || (rc = upload(&m->Js, Js)) || (rc = upload(&m->Wt, Wt)) ||
         (rc = upload(&m->W4, W4)) || (rc = upload(&m->hands_mean, hm)) || (rc = upload(&m->Jreg, Jreg)) ||
         (rc = upload(&m->Sv, build_sv(shapedirs))) ||
@@ -215,7 +219,7 @@ int ihmr_model_create(const float* v_template, const float* shapedirs, const flo
 void ihmr_model_destroy(ihmr_model_t* m) {
     if (!m) return;
     DeviceGuard guard(m->device);
-    cudaFree(m->D); cudaFree(m->DT); cudaFree(m->vtemp); cudaFree(m->Jt); cudaFree(m->Js);
+    cudaFree(m->D); cudaFree(m->DT); cudaFree(m->DTq); cudaFree(m->Dq); cudaFree(m->vtemp); cudaFree(m->Jt); cudaFree(m->Js);
     cudaFree(m->Wt); cudaFree(m->W4); cudaFree(m->hands_mean); cudaFree(m->Jreg); cudaFree(m->Sv);
     cudaFree(m->faces[0]); cudaFree(m->faces[1]); cudaFree(m->cl_tri[0]); cudaFree(m->cl_tri[1]);
     delete m;
@@ -238,8 +242,13 @@ int ihmr_model_update_shapedirs(ihmr_model_t* m, const float* shapedirs, ihmr_st
     IHMR_CUDA_OK(cudaStreamSynchronize(st));   // model mutation is the one synchronising call
     build_shape_rows(shapedirs, Jreg.data(), D, Js);
     std::vector<float> DT = transpose_D(D);
+    std::vector<float> DTq(gemm_presplit_floats(LDN, KP)), Dq(gemm_presplit_floats(KP, LDN));
+    gemm_presplit_b(DT.data(), LDN, KP, KP, DTq.data());
+    gemm_presplit_b(D.data(), KP, LDN, LDN, Dq.data());
     IHMR_CUDA_OK(cudaMemcpyAsync(m->D, D.data(), D.size() * 4, cudaMemcpyHostToDevice, st));
     IHMR_CUDA_OK(cudaMemcpyAsync(m->DT, DT.data(), DT.size() * 4, cudaMemcpyHostToDevice, st));
+    IHMR_CUDA_OK(cudaMemcpyAsync(m->DTq, DTq.data(), DTq.size() * 4, cudaMemcpyHostToDevice, st));
+    IHMR_CUDA_OK(cudaMemcpyAsync(m->Dq, Dq.data(), Dq.size() * 4, cudaMemcpyHostToDevice, st));
     IHMR_CUDA_OK(cudaMemcpyAsync(m->Js, Js.data(), Js.size() * 4, cudaMemcpyHostToDevice, st));
     const std::vector<float> sv = build_sv(shapedirs);
     IHMR_CUDA_OK(cudaMemcpyAsync(m->Sv, sv.data(), sv.size() * 4, cudaMemcpyHostToDevice, st));

@@ -19,6 +19,8 @@
 // thread issues 4 K-steps x 3 MMAs and commits to an mbarrier), then each warp drains its 32
 // TMEM lanes with tcgen05.ld and writes its rows.  Two CTAs per SM overlap one CTA's loads with
 // the other's MMAs.
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace ihmr {
@@ -137,13 +139,14 @@ __device__ __forceinline__ void store_chunk(const ChunkRegs<NITEMS>& regs, int r
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS)
 k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-              float* __restrict__ C, int ldc, const int* __restrict__ rows, const int* __restrict__ nrows) {
+              float* __restrict__ C, int ldc, const int* __restrict__ rows, const int* __restrict__ nrows,
+              const float* __restrict__ Bq) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_hi = smem;
     unsigned char* a_lo = a_hi + TC_BM * TC_BK * 4;
     unsigned char* b_hi = a_lo + TC_BM * TC_BK * 4;
     unsigned char* b_lo = b_hi + BN * TC_BK * 4;
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar, mbar_b;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -160,6 +163,7 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar_b)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -170,6 +174,16 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
 
     uint32_t parity = 0;
     const int nchunks = K / TC_BK;
+    // pre-split B: the (hi, lo) blocks of this N tile's chunk arrive by two bulk copies (first n_inst rows of each)
+    auto issue_b = [&](int ch) {
+        const float* src = Bq + ((size_t)blockIdx.x * nchunks + ch) * (2 * BN * TC_BK);
+        const uint32_t bytes = (uint32_t)n_inst * (TC_BK * 4), bar = smem_u32(&mbar_b);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2 * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(b_hi)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(b_lo)), "l"(src + BN * TC_BK), "r"(bytes), "r"(bar) : "memory");
+    };
     constexpr int A_ITEMS = TC_BM * 8 / TC_THREADS;
     ChunkRegs<A_ITEMS> ra;
     ChunkRegs<BN * 8 / TC_THREADS> rb;
@@ -182,13 +196,15 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
         rowsrc[i] = (r < rows_a) ? (rows ? rows[m0 + r] : m0 + r) : -1;
     }
     fetch_chunk_rows(ra, A, lda, rowsrc, 0, tid);
-    fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, 0, tid);
+    if (Bq) { if (tid == 0) issue_b(0); }
+    else fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, 0, tid);
     for (int ch = 0; ch < nchunks; ++ch) {
         store_chunk(ra, TC_BM, a_hi, a_lo, tid);
-        store_chunk(rb, n_inst, b_hi, b_lo, tid);
+        if (!Bq) store_chunk(rb, n_inst, b_hi, b_lo, tid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (tensor core)
         __syncthreads();
         if (tid == 0) {
+            if (Bq) mbar_wait(smem_u32(&mbar_b), (uint32_t)(ch & 1));    // this chunk's B blocks have landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks) {
@@ -204,10 +220,11 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
         }
         if (ch + 1 < nchunks) {                                      // next chunk's global loads fly while the MMAs run
             fetch_chunk_rows(ra, A, lda, rowsrc, (ch + 1) * TC_BK, tid);
-            fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, (ch + 1) * TC_BK, tid);
+            if (!Bq) fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, (ch + 1) * TC_BK, tid);
         }
         mbar_wait(smem_u32(&mbar), parity);                          // operands may be overwritten, accumulator is current
         parity ^= 1;
+        if (Bq && tid == 0 && ch + 1 < nchunks) issue_b(ch + 1);
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -442,23 +459,54 @@ int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float
 
 template <int BN>
 static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st,
-                     const int* rows, const int* nrows) {
+                     const int* rows, const int* nrows, const float* Bq) {
     const size_t smem = (size_t)(2 * TC_BM + 2 * BN) * TC_BK * 4;
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_gemm_tf32x3<BN>, smem, configured)) return rc;
     dim3 grid((Nc + BN - 1) / BN, (M + TC_BM - 1) / TC_BM);
-    k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, C, ldc, rows, nrows);
+    k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, C, ldc, rows, nrows, Bq);
     IHMR_LAUNCH_OK();
     return IHMR_OK;
 }
 
 // C[M,Nc] = A[M,K] . B[Nc,K]^T ; K % 32 == 0, Nc % 4 == 0, lda/ldb/ldc % 4 == 0
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st, const int* rows, const int* nrows) {
+                       cudaStream_t st, const int* rows, const int* nrows, const float* Bq) {
     if (M <= 0) return IHMR_OK;
     if (K % TC_BK || Nc % 4 || lda % 4 || ldb % 4 || ldc % 4) { set_error("gemm_tf32x3: unsupported shape"); return IHMR_E_INVALID; }
-    if (Nc > 160) return launch_tc<256>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows);
-    return launch_tc<160>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows);
+    if (Nc > 160) return launch_tc<256>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows, Bq);
+    return launch_tc<160>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows, Bq);
+}
+
+// Host side of the pre-split operand: for every (N tile of BN rows, K chunk of 32) a block [hi | lo], each BN x 32 floats in
+// the canonical no-swizzle K-major core-matrix layout the kernel's shared-memory descriptors expect
+// ([row / 8][K column of 16 bytes][row % 8][4 floats]); rows beyond Nc are zero.  BN follows launch_gemm_tf32x3.
+static int presplit_bn(int Nc) { return Nc > 160 ? 256 : 160; }
+size_t gemm_presplit_floats(int Nc, int K) {
+    const int BN = presplit_bn(Nc);
+    return (size_t)((Nc + BN - 1) / BN) * (K / TC_BK) * 2 * BN * TC_BK;
+}
+void gemm_presplit_b(const float* B, int Nc, int K, int ldb, float* out) {
+    const int BN = presplit_bn(Nc), ntiles = (Nc + BN - 1) / BN, nch = K / TC_BK;
+    for (int t = 0; t < ntiles; ++t)
+        for (int ch = 0; ch < nch; ++ch) {
+            float* hi = out + ((size_t)t * nch + ch) * (2 * BN * TC_BK);
+            float* lo = hi + BN * TC_BK;
+            for (int r = 0; r < BN; ++r)
+                for (int kc = 0; kc < 8; ++kc)
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = t * BN + r;
+                        const float v = row < Nc ? B[(size_t)row * ldb + ch * TC_BK + kc * 4 + j] : 0.f;
+                        uint32_t bits;
+                        memcpy(&bits, &v, 4);
+                        bits &= 0xffffe000u;
+                        float h;
+                        memcpy(&h, &bits, 4);
+                        const size_t o = (size_t)(r / 8) * (TC_SBO / 4) + kc * (TC_LBO / 4) + (r % 8) * 4 + j;
+                        hi[o] = h;
+                        lo[o] = v - h;
+                    }
+        }
 }
 
 }  // namespace ihmr

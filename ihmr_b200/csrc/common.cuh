@@ -120,6 +120,8 @@ struct ihmr_model {
     int num_sms;
     float* D;        // (KP, LDN)  rows 0..134 posedirs, 135..144 shapedirs (k-major), rest 0
     float* DT;       // (LDN, KP)  transpose of D
+    float* DTq;      // D^T pre-split hi/lo in the tensor-core operand layout: [10 N-tiles of 256][5 K-chunks][hi|lo][256 x 32]
+    float* Dq;       // D likewise for the backward contraction: [73 K-chunks][hi|lo][160 x 32]
     float* vtemp;    // (LDN)      v_template flattened, padded with 0
     float* Jt;       // (48)       J_regressor @ v_template
     float* Js;       // (10, 48)   J_regressor @ shapedirs[:, :, k]

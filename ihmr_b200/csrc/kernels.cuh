@@ -72,8 +72,13 @@ int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float
                        float* bbox = nullptr);
 // C[M,Nc] = A[M,K] . B[Nc,K]^T on tcgen05 with 3xTF32 splitting (blend_tc.cu)
 // rows / nrows (device, optional): row r of the product uses row rows[r] of A and of C, for r < *nrows <= M
+// Bq (device, optional): B pre-split into (hi, lo) and laid out as the tensor core reads it, one contiguous block per
+// (N tile, K chunk) — gemm_presplit_b() builds it on the host.  The kernel then fetches B with two bulk copies per
+// chunk (TMA, no register staging) and only stages A itself.
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st, const int* rows = nullptr, const int* nrows = nullptr);
+                       cudaStream_t st, const int* rows = nullptr, const int* nrows = nullptr, const float* Bq = nullptr);
+size_t gemm_presplit_floats(int Nc, int K);
+void gemm_presplit_b(const float* B, int Nc, int K, int ldb, float* out);      // host arrays
 // C[M,N] = A[M,K] . B[K,N] on the FP32 pipe: reference for the tensor-core path (tests only)
 int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                            cudaStream_t st);

@@ -1281,12 +1281,12 @@ int launch_pose_prep(const ihmr_model* m, int n, HandSrc src, float* X, float* A
 
 int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cudaStream_t st) {
     // off (n x 2336) = X (n x 160) . D  ==  X . (D^T)^T  with D^T (2336 x 160) K-major
-    return launch_gemm_tf32x3(n, LDN, KP, X, KP, m->DT, KP, off, LDN, st);
+    return launch_gemm_tf32x3(n, LDN, KP, X, KP, m->DT, KP, off, LDN, st, nullptr, nullptr, m->DTq);
 }
 
 int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp) {
     // dX (n x 160) = gposed (n x 2336) . D^T  with D (160 x 2336) K-major; with a dense-hand list only those rows
-    return launch_gemm_tf32x3(n, KP, LDN, gposed, LDN, m->D, LDN, dX, KP, st, sp.dense_list, sp.dense_count);
+    return launch_gemm_tf32x3(n, KP, LDN, gposed, LDN, m->D, LDN, dX, KP, st, sp.dense_list, sp.dense_count, m->Dq);
 }
 
 int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
