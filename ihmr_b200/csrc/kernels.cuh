@@ -118,6 +118,7 @@ struct SdfArgs {
     float* losses = nullptr;           // (B) or null: mask * (part_0 + part_1) / 4 (one more tiny launch)
     float box_scale = 0.6f;            // (filled by launch_sdf from the model) scale = box_scale * max bbox extent   (A2)
     int ray_axis = 0;                  // (filled by launch_sdf from the model) world axis of the parity ray          (A4)
+    bool l2_prefetch = false;          // (filled by launch_sdf) verts is 16-byte aligned: the next item's frame is prefetched into L2
 };
 size_t sdf_ws_bytes(int B);
 size_t sdf_hint_bytes(int B);

@@ -66,9 +66,6 @@ constexpr int NCL = (NF + 31) / 32; // static face clusters of <= 32 faces (49)
 #endif
 constexpr int PHI_CAP = SDF_PHI_CAP, Q_CAP = SDF_Q_CAP;
 constexpr int QSEG = Q_CAP / SDF_WARPS;   // candidate queue segment of one warp
-#ifndef SDF_L2_PREFETCH
-#define SDF_L2_PREFETCH 1
-#endif
 static_assert(PHI_CAP <= 65536, "queue entries pack the voxel index into 16 bits");
 static_assert(QSEG >= 64, "a queue segment takes at least two rounds of 32 entries");
 constexpr int SDF_SPILL = NV * 8;   // a direction evaluates at most 8 voxels per query vertex
@@ -528,11 +525,10 @@ k_sdf_dir(int B, SdfArgs a, SdfWs w, const ushort4* __restrict__ cl_r, const ush
 #pragma unroll
             for (int q = 0; q + 1 < SDF_BUCKETS; ++q) if (t >= bucket_end[q]) { k = q + 1; start = bucket_end[q]; }
             code = w.items[(size_t)k * 2 * B + (t - start)];
-#if SDF_L2_PREFETCH
             // both hands of that frame (18,672 B, 16-byte aligned) on their way from DRAM to L2 while this item is processed
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                         :: "l"(a.verts + (size_t)(code >> 1) * (2 * NV * 3)), "r"(2 * NV * 3 * 4) : "memory");
-#endif
+            if (a.l2_prefetch)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                             :: "l"(a.verts + (size_t)(code >> 1) * (2 * NV * 3)), "r"(2 * NV * 3 * 4) : "memory");
         }
         s.item = code;
     };
@@ -1329,6 +1325,7 @@ int launch_sdf(const ihmr_model* m, int B, const SdfArgs& a, cudaStream_t st) {
     IHMR_CUDA_OK(cudaMemsetAsync(w.counters, 0, (SDF_BUCKETS + 1) * 4, st));
     SdfArgs pa = a;
     pa.box_scale = m->sdf_box_scale; pa.ray_axis = m->sdf_ray_axis;       // conventions A2 / A4 of the model
+    pa.l2_prefetch = (reinterpret_cast<uintptr_t>(a.verts) & 15u) == 0;   // the bulk prefetch wants 16-byte aligned frames
     k_sdf_prep<<<(B + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, st>>>(B, pa, w);
     IHMR_LAUNCH_OK();
     const int grid = std::min(std::min(m->num_sms * ctas_per_sm[kv], SDF_MAX_GRID), 2 * B);
