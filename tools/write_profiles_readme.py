@@ -1,0 +1,140 @@
+"""Regenerates profiles/README.md from the measurement files of a round (so the tables are exactly the committed numbers).
+
+    python tools/write_profiles_readme.py [tag]        (default tag: r02)
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+
+
+def load(name):
+    path = os.path.join(P, f"{tag}_{name}.json")
+    return json.load(open(path)) if os.path.exists(path) else None
+
+
+n1, ref, c2, c3, c5, f8192, f512 = (load(k) for k in ("bench_n1", "bench_reference", "bench_cfg2", "bench_cfg3", "bench_cfg5",
+                                                      "bench_f8192", "bench_f512"))
+scale = {n: load(f"bench_n{n}") for n in (2, 4, 8)}
+strong = {n: load(f"bench_strong_n{n}") for n in (2, 4, 8)}
+out = []
+w = out.append
+w(f"# profiles — round 2 (B200, sm_100a)\n")
+w("All numbers were produced by `gpurun` calls on a B200 (SM clock 1965 MHz during the timed regions, no throttle reason\n"
+  "active: the `clocks` object of every bench line). Everything here is written by `tools/final_measurements.sh`,\n"
+  "`tools/collect_profiles.sh` and `tools/summarise_ncu.py`; this file by `tools/write_profiles_readme.py`. Round-1 files\n"
+  "(`r01_*`, `traffic.json`) are kept for comparison.\n")
+w("| file | what |\n|---|---|")
+w(f"| `{tag}_bench_n1.json` | `python bench.py --steps 3 --warmup 3` (BASELINE config 4 at N=1: 65536 frames x 100 iterations) |")
+w(f"| `{tag}_bench_reference.json` | `python bench.py --impl reference --steps 2 --warmup 1` (oracle port of the reference loop, all host threads) |")
+w(f"| `{tag}_bench_cfg2.json`, `_cfg3.json`, `_cfg5.json` | `bench.py --config 2|3|5`: MANO op, penetration-op sweep, worst-case collisions |")
+w(f"| `{tag}_bench_f8192.json`, `_f512.json` | config 4 with 8192 / 512 frames per GPU (strong-scaling share at N=8; the reference's shipped batch) |")
+w(f"| `{tag}_bench_n2/4/8.json`, `{tag}_bench_strong_n*.json` | the same under `torch.distributed.run`, weak (65536 frames per GPU) and strong (65536 frames in total) scaling, where run |")
+w(f"| `{tag}_launches.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of one whole step (cold-cache, serialised: read the SHARES) |")
+w(f"| `{tag}_ncu_summary.csv` | one row per stage x kernel of a steady-state iteration (SpeedOfLight, memory, scheduler, occupancy, pipe sections) |")
+w(f"| `{tag}_traffic.json`, `{tag}_issue.json` | DRAM bytes per launch unit and the issue-slot utilisation of `k_sdf_dir` from that capture (read by `bench.py`) |")
+w(f"| `{tag}_sdf_details.txt`, `{tag}_sdf_source_lines.txt` | `ncu --set full --import-source on` of the steady-state stage-2 launch of `k_sdf_dir`: details page, and stall samples / executed instructions per source line |")
+w(f"| `{tag}_sass_opcodes.csv` | SASS opcode histogram of every kernel of the library (`tools/sass_histogram.py`): UTCHMMA / LDTM / UTCBAR / UBLKCP / ... |")
+w("| `sanitizer/` | compute-sanitizer memcheck / racecheck / initcheck / synccheck over every kernel, regular and small-capacity library |\n")
+
+if n1:
+    sr, rf = n1["step_roofline"], n1["roofline"]
+    w("## Headline (1 x B200, BASELINE config 4)\n")
+    w("| quantity | value |\n|---|---|")
+    w(f"| frames refined / s, batch resident in HBM (`value`) | **{n1['value']:,.0f}** ({n1['ms_per_step']:.1f} ms per 65536-frame step, {n1['us_per_frame_iteration']:.4f} us per frame-iteration) |")
+    e = n1["e2e"]
+    w(f"| frames refined / s end to end through `OptimizeModel.run_pipelined` with host buffers (`e2e`; H2D {e['h2d_bytes_per_step']/1e6:.0f} MB + D2H {e['d2h_bytes_per_step']/1e9:.2f} GB per step inside the timed region, {e['steps']} steps) | **{e['value']:,.0f}** ({100 * (1 - e['value'] / n1['value']):.1f} % below `value`) |")
+    w(f"| kernels launched per step (direct + replayed from CUDA graphs) | {n1['gpu_launches']} |")
+    w(f"| dominant kernel class | `{rf['kernel']}`: {rf['avg_launch_ms']:.2f} ms per launch on average over the four stages = {rf['achieved']:.0f} GB/s against the algorithmic bytes = **{rf['frac']:.3f}** of the measured HBM peak ({rf['peak']:.0f} GB/s); bound: {rf['bound']} |")
+    w(f"| fused step | {sr['iteration_ms']:.2f} ms per average iteration = {sr['achieved']:.0f} GB/s against 76,388 B per frame-iteration = **{sr['frac']:.3f}** of the HBM peak |")
+    if n1.get("cpu_baseline"):
+        cb = n1["cpu_baseline"]
+        w(f"| CPU baseline inside the same run (`cpu_baseline`, {cb['kind']}) | {cb['value']:.3f} frames/s on {cb['cores']} host threads ({cb['sample']}) |")
+    if ref:
+        w(f"| reference arm (`--impl reference`) | {ref['value']:.3f} frames/s ({ref['cpu_baseline']['sample']}) |")
+    w("")
+    w("Round 1 (same config, `r01_bench_n1.json`): 71,952 frames/s resident, 69,062 end to end, penetration kernel 6.7 ms.\n")
+    w("Live CUDA-event measurement inside `bench.py` (`step_roofline.kernel_ms_per_stage`, ms per steady-state iteration; the slots are\n"
+      "named after the generic kernels — in stage 1 the `skin_fwd` / `pose_bwd` slots hold `k_rigid_fwd` / `k_rigid_bwd`, in stage 3 the\n"
+      "`skin_fwd` / `skin_bwd` slots hold `k_shape_fwd` / `k_shape_bwd`; `sdf` = `k_sdf_prep` + `k_sdf_dir`):\n")
+    keys = list(sr["kernel_ms_per_stage"][0].keys())
+    w("| stage | " + " | ".join(keys) + " | sum |\n|---|" + "---|" * (len(keys) + 1))
+    names = ["0 trans (static-grid cache)", "1 orients (rigid path)", "2 poses (generic path)", "3 shapes (affine path)"]
+    for nm, st in zip(names, sr["kernel_ms_per_stage"]):
+        w(f"| {nm} | " + " | ".join("–" if st[k] < 0.01 else f"{st[k]:.2f}" for k in keys) + f" | {sum(st.values()):.2f} |")
+    w("")
+
+lpath = os.path.join(P, f"{tag}_launches.csv")
+if os.path.exists(lpath):
+    w("## Launch list of one whole step (ncu, serialised; shares)\n")
+    w(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarise_launches.py"), lpath], capture_output=True, text=True).stdout)
+
+spath = os.path.join(P, f"{tag}_ncu_summary.csv")
+if os.path.exists(spath):
+    rows = list(csv.DictReader(open(spath)))
+    w("## ncu, steady-state iteration of every stage (65536 frames; `" + f"{tag}_ncu_summary.csv`)\n")
+    w("| stage | kernel | ms | DRAM B / unit | DRAM % | issue % | IPC / SM | lanes / inst | FMA % | ALU % | tensor % | LSU % | regs |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+
+    def f(r, k, fmt="{:.1f}"):
+        try:
+            return fmt.format(float(r[k]))
+        except (ValueError, KeyError, TypeError):
+            return "–"
+    seen = set()
+    for r in rows:
+        key = (r["kernel"], r["stage"])
+        generic = r["kernel"].split("<")[0] in ("k_pose_prep", "k_gemm_tf32x3", "k_skin_fwd_tc") and r["stage"] != "2" and not (r["kernel"].startswith("k_pose_prep") and r["stage"] == "3")
+        if generic or key in seen:
+            continue                     # the warm generic forward repeats in every stage: list it once (stage 2)
+        seen.add(key)
+        w(f"| {r['stage']} | `{r['kernel']}` | {f(r, 'ms', '{:.3f}')} | {f(r, 'dram_bytes_per_unit', '{:.0f}')} ({r['unit']}) | {f(r, 'dram_pct')} | {f(r, 'issue_active_pct')} | "
+          f"{f(r, 'ipc_per_sm', '{:.2f}')} | {f(r, 'lanes_per_inst')} | {f(r, 'fma_pipe_pct')} | {f(r, 'alu_pipe_pct')} | {f(r, 'tensor_pipe_pct')} | {f(r, 'lsu_wavefronts_pct')} | {f(r, 'registers', '{:.0f}')} |")
+    w("")
+
+if c2:
+    w("## BASELINE config 2 — MANO layer forward + backward, 2 x 4096 hands\n")
+    w(f"{c2['value']:.4f} us/hand (forward {c2['fwd_ms']:.3f} ms + backward {c2['bwd_ms']:.3f} ms per 8192 hands, {c2['gpu_launches']} launches); "
+      f"{c2['roofline']['achieved']:.1f} TFLOP/s = {100 * c2['roofline']['frac']:.1f} % of the FFMA peak measured in the same run "
+      f"({c2['roofline']['peak']:.1f} TFLOP/s, `ihmr_measure_fp32_peak`); {c2['hbm']['achieved']:.0f} GB/s against the op-boundary bytes "
+      f"(19,520 B/hand; {100 * c2['hbm']['frac']:.1f} % of HBM); blend contraction {c2['tensor']['achieved']:.1f} algorithmic TFLOP/s on tcgen05 (3xTF32).\n")
+if c3:
+    w("## BASELINE config 3 — penetration op forward + backward, B = 1 ... 16384 (stateless calls: no hints carried)\n")
+    w("| frames | mode | ms | us / frame | GB/s vs 43,572 B/frame | voxels / frame | exact tests / frame | exact tests / s |\n|---|---|---|---|---|---|---|---|")
+    for s in c3["sweep"]:
+        w(f"| {s['frames']} | {s['mode']} | {s['ms']:.3f} | {s['us_per_frame']:.3f} | {s['GBps_vs_alg']:.1f} | {s['voxels_per_frame']:.0f} | {s['exact_tests_per_frame']:.0f} | {s['tests_per_s'] / 1e9:.2f} G |")
+    w("")
+if c5 and n1:
+    w("## BASELINE config 5 — near-coincident hands (every frame collides)\n")
+    w(f"{c5['value']:,.0f} frames/s on one B200 ({c5['ms_per_step']:.0f} ms per 65536-frame step, e2e {c5['e2e']['value']:,.0f}): {n1['value'] / c5['value']:.2f}x slower than config 4.\n")
+if f8192 and f512 and n1:
+    w("## Smaller batches per GPU (CUDA-graph replay of the stage calls)\n")
+    w("| frames per GPU | frames/s | ms per step | per-frame rate vs 65536 frames |\n|---|---|---|---|")
+    for d, nfr in ((n1, 65536), (f8192, 8192), (f512, 512)):
+        w(f"| {nfr} | {d['value']:,.0f} | {d['ms_per_step']:.1f} | {100 * d['value'] / n1['value']:.0f} % |")
+    w("")
+if any(scale.values()) or any(strong.values()):
+    w("## Multi-GPU (one process per GPU, frames sharded, one all-gather per step)\n")
+    w("| GPUs | scaling | frames/s (`value`) | ms per step | e2e frames/s | vs N x the 1-GPU value / e2e |\n|---|---|---|---|---|---|")
+    for n, d in scale.items():
+        if d:
+            w(f"| {n} | weak (65536 per GPU) | {d['value']:,.0f} | {d['ms_per_step']:.1f} | {d['e2e']['value']:,.0f} | {d['value'] / (n * n1['value']):.3f} / {d['e2e']['value'] / (n * n1['e2e']['value']):.3f} |")
+    for n, d in strong.items():
+        if d:
+            w(f"| {n} | strong (65536 in total) | {d['value']:,.0f} | {d['ms_per_step']:.1f} | {d['e2e']['value']:,.0f} | {d['value'] / (n * n1['value']):.3f} / {d['e2e']['value'] / (n * n1['e2e']['value']):.3f} |")
+    w("")
+ipath = os.path.join(P, f"{tag}_issue.json")
+if os.path.exists(ipath):
+    i = json.load(open(ipath)).get("sdf")
+    if i:
+        w("## `k_sdf_dir` (steady state, stage 2) in one paragraph\n")
+        w(f"Issue slots {i['issue_active_pct']:.1f} % busy, IPC {i['ipc_per_sm']:.2f} of 4 per SM, {i['lanes_per_inst']:.1f} active lanes per instruction, "
+          f"{i['warps_active_pct']:.0f} % of the warp slots occupied (4 CTAs of 256 threads, 64 registers, 54 KB of shared memory), DRAM {i['dram_pct']:.1f} % busy. "
+          f"`{tag}_sdf_source_lines.txt` lists where the stall samples fall: block barriers between the phases of an item, fixed-latency "
+          "dependencies in the integer box tests, shared-memory latency; no pipe is above ~50 %.\n")
+open(os.path.join(P, "README.md"), "w").write("\n".join(out))
+print("wrote profiles/README.md,", len(out), "blocks")
