@@ -13,6 +13,9 @@ namespace ihmr {
 struct Tree {
     int8_t parent[16];
     int8_t depth[16];
+    int8_t nchild[16];          // children of every joint (all one level deeper), ascending joint order
+    int8_t child[16][15];
+    int8_t maxchild[16];        // [level]: most children any joint of depth level - 1 has
     int maxdepth;
 };
 
@@ -23,6 +26,14 @@ static Tree make_tree(const int* parents) {
         t.parent[j] = (int8_t)(parents[j] < 0 ? 0 : parents[j]);
         t.depth[j] = (int8_t)(parents[j] < 0 ? 0 : t.depth[parents[j]] + 1);
         if (t.depth[j] > t.maxdepth) t.maxdepth = t.depth[j];
+        t.nchild[j] = 0;
+        t.maxchild[j] = 0;
+        for (int k = 0; k < 15; ++k) t.child[j][k] = -1;
+    }
+    for (int ch = 1; ch < NJ; ++ch) {
+        const int p = t.parent[ch];
+        t.child[p][t.nchild[p]++] = (int8_t)ch;
+        if (t.nchild[p] > t.maxchild[t.depth[ch]]) t.maxchild[t.depth[ch]] = t.nchild[p];
     }
     return t;
 }
@@ -272,12 +283,13 @@ __global__ void __launch_bounds__(128) k_pose_bwd(int n, HandSrc src, const floa
 #pragma unroll
             for (int i = 0; i < 15; ++i) c[i] = 0.f;
         }
-        for (int ch = 1; ch < NJ; ++ch) {
-            const bool mine = (tree.parent[ch] == j) && (tree.depth[ch] == level);
+        // (a joint's children are exactly one level deeper: each lane reads its own k-th child, ascending order)
+        for (int k = 0; k < tree.maxchild[level]; ++k) {
+            const int ch = (dep == level - 1) ? tree.child[j][k] : -1;
 #pragma unroll
             for (int i = 0; i < 15; ++i) {
-                float v = __shfl_sync(0xffffffffu, c[i], base + ch);
-                if (mine) {
+                float v = __shfl_sync(0xffffffffu, c[i], base + max(ch, 0));
+                if (ch >= 0) {
                     if (i < 9) dRg[i] += v;
                     else if (i < 12) dtg[i - 9] += v;
                     else dJ[i - 12] += v;
