@@ -49,14 +49,23 @@ __device__ __forceinline__ void cross3(const float* a, const float* b, float* c)
     c[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-// fixed-order sum over the 64 threads of the block; result in every thread
-__device__ __forceinline__ float block64_sum(float v, float* red) {
+// fixed-order sums over the 64 threads of the block for N values behind one pair of barriers (warp butterfly, then
+// warp 0 + warp 1); results in every thread
+template <int N>
+__device__ __forceinline__ void block64_sum_n(float (&v)[N], float* red) {
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) red[(threadIdx.x >> 5) * N + i] = v[i];
+    }
     __syncthreads();
-    return red[0] + red[1];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = red[i] + red[N + i];
 }
 
 // Online form of filter_by_losses + select_params (src/utils/opt_utils.py:104-152) for one frame and one
@@ -100,7 +109,7 @@ __global__ void k_select_snapshots(int S, int B, const float* __restrict__ crit,
 __global__ void __launch_bounds__(FL_THREADS) k_frame_loss(FrameLossArgs a) {
     __shared__ float sJ[42][3];     // joints at the current alignment stage
     __shared__ float sG[42][3];     // gradient w.r.t. the aligned joints
-    __shared__ float red[2];
+    __shared__ float red[2 * 9];
     const int b = blockIdx.x, t = threadIdx.x;
     const bool isj = t < 42;
     const int hand = isj ? t / 21 : 0, k = isj ? t % 21 : 0;
@@ -218,24 +227,26 @@ __global__ void __launch_bounds__(FL_THREADS) k_frame_loss(FrameLossArgs a) {
     if (isj) { ga[0] += sG[t][0]; ga[1] += sG[t][1]; ga[2] += sG[t][2]; }
     // ---- back through the two alignments: g <- g - e_root * sum(g)
     {
-        float s0 = block64_sum(ga[0], red), s1 = block64_sum(ga[1], red), s2 = block64_sum(ga[2], red);
-        if (r2 >= 0 && t == r2) { ga[0] -= s0; ga[1] -= s1; ga[2] -= s2; }
-        s0 = block64_sum(ga[0], red); s1 = block64_sum(ga[1], red); s2 = block64_sum(ga[2], red);
-        if (r1 >= 0 && t == r1) { ga[0] -= s0; ga[1] -= s1; ga[2] -= s2; }
+        float sm[3] = {ga[0], ga[1], ga[2]};
+        block64_sum_n(sm, red);
+        if (r2 >= 0 && t == r2) { ga[0] -= sm[0]; ga[1] -= sm[1]; ga[2] -= sm[2]; }
+        sm[0] = ga[0]; sm[1] = ga[1]; sm[2] = ga[2];
+        block64_sum_n(sm, red);
+        if (r1 >= 0 && t == r1) { ga[0] -= sm[0]; ga[1] -= sm[1]; ga[2] -= sm[2]; }
     }
     gJ[0] += ga[0]; gJ[1] += ga[1]; gJ[2] += ga[2];
     if (a.dense_list && t < 2 && !a.gzero[b * 2 + t]) a.dense_list[atomicAdd(a.dense_count, 1)] = b * 2 + t;
     // ---- shift gradient: all left-hand joints move with it
-    float gs[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) gs[c] = block64_sum((isj && hand == 1) ? gJ[c] : 0.f, red);
+    //      and the per-frame scalar terms, all nine sums behind one pair of barriers
+    const bool lj = isj && hand == 1;
+    float sums[9] = {lj ? gJ[0] : 0.f, lj ? gJ[1] : 0.f, lj ? gJ[2] : 0.f, l2d, l3d, lfin, dcs, dcx, dcy};
+    block64_sum_n(sums, red);
+    float gs[3] = {sums[0], sums[1], sums[2]};
     if (a.gshift_col) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) gs[c] += a.gshift_col[(size_t)b * 3 + c];
     }
-    // ---- per-frame scalar terms
-    const float sum2d = block64_sum(l2d, red), sum3d = block64_sum(l3d, red), sumfin = block64_sum(lfin, red);
-    const float gcs = block64_sum(dcs, red), gcx = block64_sum(dcx, red), gcy = block64_sum(dcy, red);
+    const float sum2d = sums[3], sum3d = sums[4], sumfin = sums[5], gcs = sums[6], gcx = sums[7], gcy = sums[8];
 
     if (isj && a.gjoints16) {
         float g[3] = {gJ[0], gJ[1], gJ[2]};
