@@ -491,11 +491,11 @@ __global__ void k_sdf_finish(int B, const float* __restrict__ parts, const float
         atomicAdd(&a.stats[b * 32 + 18 + (i)], (int)(t_now - t_prev));                    \
         t_prev = t_now;                                                                   \
     }
-// stats (B,32) int32, diagnostics only: [2h] voxels evaluated with grid hand h, [2h+1] search rounds,
-// [4+h] query vertices inside the grid box, [6] (voxel, cluster) pairs, [7] exact candidates, [8] marked voxels,
-// [9] ray items, [10] passes, [11] ray queue segments flushed early (full), [12] candidate queue segments flushed
-// early (full), [16+h] direction finished by k_sdf_prep, [19..27] cycles per phase (mark, face boxes,
-// parity, scan, worklist, seeds + candidates, exact tests, finish, sample + outputs)
+// stats (B,32) int32, diagnostics only: [2h] voxels evaluated with grid hand h, [4+h] query vertices inside the grid
+// box, [6] (voxel, cluster) pairs, [7] exact candidates, [8] marked voxels, [9] ray items, [10] passes, [11] ray queue
+// segments flushed early (full), [12] candidate queue segments flushed early (full), [13] voxels answered by the
+// static-grid cache, [14+h] cost proxy of the direction, [16+h] direction finished by k_sdf_prep, [19..27] cycles per
+// phase (mark, face boxes, parity, scan, worklist + seeds, unused, candidate search + exact tests, finish, sample + outputs)
 
 // kStatic = false compiles the static-grid cache out (stages in which both hands move)
 // kStats = true only for ihmr_sdf_stats (tools, capacity tests): the counters cost ~300 instructions of code
