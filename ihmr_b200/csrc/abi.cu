@@ -304,7 +304,7 @@ int ihmr_mano_backward(const ihmr_model_t* m, int n, const float* global_orient,
     if ((rc = launch_pose_prep(m, n, src, w.X, w.A, w.joints, st))) return rc;
     if ((rc = launch_blend_fwd(m, n, w.X, w.off, st))) return rc;
     if ((rc = launch_skin_bwd(m, n, w.off, w.A, grad_vertices, nullptr, w.gposed, w.dA, st))) return rc;
-    if ((rc = launch_blend_bwd(m, n, w.gposed, w.dX, st))) return rc;
+    if ((rc = launch_blend_bwd(m, n, w.gposed, w.dX, st, SparseGrad(), w.off))) return rc;
     HandGrad hg;
     hg.orient = grad_global_orient; hg.pose = grad_hand_pose; hg.betas = grad_betas;
     return launch_pose_bwd(m, n, src, w.dA, grad_joints, w.dX, hg, st);

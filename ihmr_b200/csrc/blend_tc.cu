@@ -140,7 +140,7 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS)
 k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
               float* __restrict__ C, int ldc, const int* __restrict__ rows, const int* __restrict__ nrows,
-              const float* __restrict__ Bq) {
+              const float* __restrict__ Bq, size_t part_stride) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_hi = smem;
     unsigned char* a_lo = a_hi + TC_BM * TC_BK * 4;
@@ -174,6 +174,10 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
 
     uint32_t parity = 0;
     const int nchunks = K / TC_BK;
+    // split K (gridDim.z > 1): this CTA takes a contiguous range of chunks and writes a partial product into its own
+    // copy of C (part_stride floats apart); launch_gemm_tf32x3 sums the copies in fixed order afterwards
+    const int ch_begin = (int)(((long long)nchunks * blockIdx.z) / gridDim.z), ch_end = (int)(((long long)nchunks * (blockIdx.z + 1)) / gridDim.z);
+    C += (size_t)blockIdx.z * part_stride;
     // pre-split B: the (hi, lo) blocks of this N tile's chunk arrive by two bulk copies (first n_inst rows of each)
     auto issue_b = [&](int ch) {
         const float* src = Bq + ((size_t)blockIdx.x * nchunks + ch) * (2 * BN * TC_BK);
@@ -195,36 +199,36 @@ k_gemm_tf32x3(int M, int Nc, int K, const float* __restrict__ A, int lda, const 
         item_coords(tid + i * TC_THREADS, r, kc, off);
         rowsrc[i] = (r < rows_a) ? (rows ? rows[m0 + r] : m0 + r) : -1;
     }
-    fetch_chunk_rows(ra, A, lda, rowsrc, 0, tid);
-    if (Bq) { if (tid == 0) issue_b(0); }
-    else fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, 0, tid);
-    for (int ch = 0; ch < nchunks; ++ch) {
+    fetch_chunk_rows(ra, A, lda, rowsrc, ch_begin * TC_BK, tid);
+    if (Bq) { if (tid == 0) issue_b(ch_begin); }
+    else fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, ch_begin * TC_BK, tid);
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
         store_chunk(ra, TC_BM, a_hi, a_lo, tid);
         if (!Bq) store_chunk(rb, n_inst, b_hi, b_lo, tid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (tensor core)
         __syncthreads();
         if (tid == 0) {
-            if (Bq) mbar_wait(smem_u32(&mbar_b), (uint32_t)(ch & 1));    // this chunk's B blocks have landed
+            if (Bq) mbar_wait(smem_u32(&mbar_b), (uint32_t)((ch - ch_begin) & 1));    // this chunk's B blocks have landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks) {
                 const uint32_t koff = ks * 2 * TC_LBO;               // 8 tf32 = two 16-byte core-matrix columns
                 const uint64_t ah = umma_desc(smem_u32(a_hi) + koff), al = umma_desc(smem_u32(a_lo) + koff);
                 const uint64_t bh = umma_desc(smem_u32(b_hi) + koff), bl = umma_desc(smem_u32(b_lo) + koff);
-                umma_tf32(tmem_d, ah, bh, idesc, ch > 0 || ks > 0);
+                umma_tf32(tmem_d, ah, bh, idesc, ch > ch_begin || ks > 0);
                 umma_tf32(tmem_d, al, bh, idesc, true);
                 umma_tf32(tmem_d, ah, bl, idesc, true);
             }
             // arrives on the mbarrier when all MMAs issued so far have completed (implies fence::before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
         }
-        if (ch + 1 < nchunks) {                                      // next chunk's global loads fly while the MMAs run
+        if (ch + 1 < ch_end) {                                       // next chunk's global loads fly while the MMAs run
             fetch_chunk_rows(ra, A, lda, rowsrc, (ch + 1) * TC_BK, tid);
             if (!Bq) fetch_chunk(rb, B, ldb, n0, rows_b, n_inst, (ch + 1) * TC_BK, tid);
         }
         mbar_wait(smem_u32(&mbar), parity);                          // operands may be overwritten, accumulator is current
         parity ^= 1;
-        if (Bq && tid == 0 && ch + 1 < nchunks) issue_b(ch + 1);
+        if (Bq && tid == 0 && ch + 1 < ch_end) issue_b(ch + 1);
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -457,25 +461,50 @@ int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float
     return IHMR_OK;
 }
 
+// C[row] = sum over the ksplit partial products, fixed order (row list as in the contraction)
+__global__ void k_splitk_sum(int M, int Nc, int ksplit, const float* __restrict__ parts, size_t part_stride, float* __restrict__ C,
+                             int ldc, const int* __restrict__ rows, const int* __restrict__ nrows) {
+    if (nrows) M = min(M, *nrows);
+    const int per_row = Nc / 4;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * per_row) return;
+    const int r = (int)(i / per_row), c4 = (int)(i % per_row);
+    const size_t o = (size_t)(rows ? rows[r] : r) * ldc + c4 * 4;
+    float4 acc = *reinterpret_cast<const float4*>(parts + o);
+    for (int z = 1; z < ksplit; ++z) {
+        const float4 v = *reinterpret_cast<const float4*>(parts + (size_t)z * part_stride + o);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(C + o) = acc;
+}
+
 template <int BN>
 static int launch_tc(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, cudaStream_t st,
-                     const int* rows, const int* nrows, const float* Bq) {
+                     const int* rows, const int* nrows, const float* Bq, int ksplit, float* parts, size_t part_stride) {
     const size_t smem = (size_t)(2 * TC_BM + 2 * BN) * TC_BK * 4;
     static unsigned long long configured = 0ull;
     if (int rc = ensure_dynamic_smem(k_gemm_tf32x3<BN>, smem, configured)) return rc;
-    dim3 grid((Nc + BN - 1) / BN, (M + TC_BM - 1) / TC_BM);
-    k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, C, ldc, rows, nrows, Bq);
+    dim3 grid((Nc + BN - 1) / BN, (M + TC_BM - 1) / TC_BM, ksplit);
+    k_gemm_tf32x3<BN><<<grid, TC_THREADS, smem, st>>>(M, Nc, K, A, lda, B, ldb, ksplit > 1 ? parts : C, ldc, rows, nrows, Bq,
+                                                      ksplit > 1 ? part_stride : 0);
     IHMR_LAUNCH_OK();
+    if (ksplit > 1) {
+        const size_t total = (size_t)M * (Nc / 4);
+        k_splitk_sum<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(M, Nc, ksplit, parts, part_stride, C, ldc, rows, nrows);
+        IHMR_LAUNCH_OK();
+    }
     return IHMR_OK;
 }
 
 // C[M,Nc] = A[M,K] . B[Nc,K]^T ; K % 32 == 0, Nc % 4 == 0, lda/ldb/ldc % 4 == 0
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st, const int* rows, const int* nrows, const float* Bq) {
+                       cudaStream_t st, const int* rows, const int* nrows, const float* Bq, int ksplit, float* parts) {
     if (M <= 0) return IHMR_OK;
     if (K % TC_BK || Nc % 4 || lda % 4 || ldb % 4 || ldc % 4) { set_error("gemm_tf32x3: unsupported shape"); return IHMR_E_INVALID; }
-    if (Nc > 160) return launch_tc<256>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows, Bq);
-    return launch_tc<160>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows, Bq);
+    if (ksplit < 1 || ksplit > K / TC_BK || (ksplit > 1 && !parts)) { set_error("gemm_tf32x3: bad K split"); return IHMR_E_INVALID; }
+    const size_t part_stride = (size_t)M * ldc;          // one full copy of C per K slice (rows index the same space)
+    if (Nc > 160) return launch_tc<256>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows, Bq, ksplit, parts, part_stride);
+    return launch_tc<160>(M, Nc, K, A, lda, B, ldb, C, ldc, st, rows, nrows, Bq, ksplit, parts, part_stride);
 }
 
 // Host side of the pre-split operand: for every (N tile of BN rows, K chunk of 32) a block [hi | lo], each BN x 32 floats in

@@ -53,7 +53,10 @@ int launch_skin_bwd(const ihmr_model* m, int n, const float* off, const float* A
                     const float* gtips, float* gposed, float* dA, cudaStream_t st, SparseGrad sp = SparseGrad(),
                     float* dX = nullptr);
 // With sp.dense_list: only the listed rows of gposed are contracted (and only their dX rows written).
-int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp = SparseGrad());
+// scratch: (n, 2336) floats free at this point (the blend offsets `off`, dead after the skinning backward): holds the
+// K-split partial products
+int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp = SparseGrad(),
+                     float* scratch = nullptr);
 // orientation-only stages (fused layout only): cache L = R0^T (x - J0), then x = R0 L + J0 and its backward
 int launch_rigid_prep(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st);
 int launch_rigid_fwd(int n, HandSrc src, float* verts, float* joints, float* Lv, float* Lj, cudaStream_t st,
@@ -75,8 +78,12 @@ int launch_skin_fwd_tc(const ihmr_model* m, int n, const float* off, const float
 // Bq (device, optional): B pre-split into (hi, lo) and laid out as the tensor core reads it, one contiguous block per
 // (N tile, K chunk) — gemm_presplit_b() builds it on the host.  The kernel then fetches B with two bulk copies per
 // chunk (TMA, no register staging) and only stages A itself.
+// ksplit > 1: K is cut into ksplit contiguous slices computed by separate CTAs into `parts` (ksplit copies of C, M * ldc
+// floats each) and summed in fixed order by a second kernel — for a long K with few row tiles (the blend backward); the
+// split must not depend on the batch size if results are to be independent of sharding.
 int launch_gemm_tf32x3(int M, int Nc, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                       cudaStream_t st, const int* rows = nullptr, const int* nrows = nullptr, const float* Bq = nullptr);
+                       cudaStream_t st, const int* rows = nullptr, const int* nrows = nullptr, const float* Bq = nullptr,
+                       int ksplit = 1, float* parts = nullptr);
 size_t gemm_presplit_floats(int Nc, int K);
 void gemm_presplit_b(const float* B, int Nc, int K, int ldb, float* out);      // host arrays
 // C[M,N] = A[M,K] . B[K,N] on the FP32 pipe: reference for the tensor-core path (tests only)

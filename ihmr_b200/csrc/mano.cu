@@ -1296,9 +1296,14 @@ int launch_blend_fwd(const ihmr_model* m, int n, const float* X, float* off, cud
     return launch_gemm_tf32x3(n, LDN, KP, X, KP, m->DT, KP, off, LDN, st, nullptr, nullptr, m->DTq);
 }
 
-int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp) {
-    // dX (n x 160) = gposed (n x 2336) . D^T  with D (160 x 2336) K-major; with a dense-hand list only those rows
-    return launch_gemm_tf32x3(n, KP, LDN, gposed, LDN, m->D, LDN, dX, KP, st, sp.dense_list, sp.dense_count, m->Dq);
+constexpr int BLEND_BWD_KSPLIT = 4;     // fixed: the K = 2336 contraction is cut the same way whatever the batch size
+
+int launch_blend_bwd(const ihmr_model* m, int n, const float* gposed, float* dX, cudaStream_t st, SparseGrad sp, float* scratch) {
+    // dX (n x 160) = gposed (n x 2336) . D^T  with D (160 x 2336) K-major; with a dense-hand list only those rows.
+    // 73 K-chunks per row tile: cut into four slices (four times the CTAs, which is what small and medium batches lack)
+    static_assert((size_t)BLEND_BWD_KSPLIT * KP <= (size_t)LDN, "the partial products fit the scratch rows");
+    return launch_gemm_tf32x3(n, KP, LDN, gposed, LDN, m->D, LDN, dX, KP, st, sp.dense_list, sp.dense_count, m->Dq,
+                              scratch ? BLEND_BWD_KSPLIT : 1, scratch);
 }
 
 int launch_sgemm_reference(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

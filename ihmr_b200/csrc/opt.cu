@@ -624,7 +624,7 @@ static int value_and_grad(const ihmr_model* m, int B, int bs_norm, const float* 
     if (plan.mano_bwd && !plan.shape && (rc = launch_skin_bwd(m, 2 * B, w.mano.off, w.mano.A, w.gverts, w.gtips, w.mano.gposed, w.mano.dA, st, sp, w.mano.dX))) return rc;
     if (plan.shape && (rc = launch_shape_bwd(m, 2 * B, w.shape_cache, w.gverts, w.gtips, w.mano.dA, w.mano.dX, st, sp))) return rc;
     IHMR_TICK(prof, 6);
-    if (plan.blend_bwd && (rc = launch_blend_bwd(m, 2 * B, w.mano.gposed, w.mano.dX, st, sp))) return rc;
+    if (plan.blend_bwd && (rc = launch_blend_bwd(m, 2 * B, w.mano.gposed, w.mano.dX, st, sp, w.mano.off))) return rc;
     IHMR_TICK(prof, 7);
     if (plan.rigid && (rc = launch_rigid_bwd(2 * B, src, w.gverts, w.gtips, w.gjoints, w.mano.gposed, w.mano.dA, w.grad, st, sp))) return rc;
     HandGrad hg;
