@@ -431,9 +431,9 @@ def main():
 
     # end to end through the public API: every step copies its inputs from pinned host memory and its results back
     # (run_pipelined overlaps those copies with the neighbouring steps' compute); the all-gather is part of each step
-    # (the first H2D and the last D2H of a run are exposed; a production run streams many batches, so the timed run is
-    # at least six steps long)
-    e2e_steps = max(6, args.steps)
+    # (the first H2D and the last D2H of a run are exposed; a production run streams hundreds of batches, so the timed
+    # run is at least twelve steps long)
+    e2e_steps = max(12, args.steps)
     d2h_box = [0]
 
     def e2e_run(nsteps=None):
