@@ -15,7 +15,9 @@ from ihmr_b200 import dist as idist
 from ihmr_b200 import synthetic
 from oracle import mano_oracle, sdf_oracle
 
-COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+# derandomize: the same examples in every run (the driver's runs are then the runs these were developed against)
+COMMON = dict(deadline=None, derandomize=True, database=None,
+              suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 
 # ------------------------------------------------------------------------------------------ host logic (CPU)
