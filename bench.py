@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--mode", default=None, choices=["typical", "collision"], help="frame generator (default: by config)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per timed step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="length of the timed end-to-end run (default: max(12, --steps))")
     args = ap.parse_args()
     if args.mode is None:
         args.mode = "collision" if args.config == 5 else "typical"
@@ -433,7 +434,7 @@ def main():
     # (run_pipelined overlaps those copies with the neighbouring steps' compute); the all-gather is part of each step
     # (the first H2D and the last D2H of a run are exposed; a production run streams hundreds of batches, so the timed
     # run is at least twelve steps long)
-    e2e_steps = max(12, args.steps)
+    e2e_steps = args.e2e_steps or max(12, args.steps)
     d2h_box = [0]
 
     def e2e_run(nsteps=None):

@@ -34,6 +34,7 @@ w("| file | what |\n|---|---|")
 w(f"| `{tag}_bench_n1.json` | `python bench.py --steps 3 --warmup 3` (BASELINE config 4 at N=1: 65536 frames x 100 iterations) |")
 w(f"| `{tag}_bench_reference.json` | `python bench.py --impl reference --steps 2 --warmup 1` (oracle port of the reference loop, all host threads) |")
 w(f"| `{tag}_bench_cfg2.json`, `_cfg3.json`, `_cfg5.json` | `bench.py --config 2|3|5`: MANO op, penetration-op sweep, worst-case collisions |")
+w(f"| `{tag}_bench_cfg5_n8.json` | config 5 on 8 GPUs (`torch.distributed.run`, 65536 near-coincident frames per GPU) |")
 w(f"| `{tag}_bench_f8192.json`, `_f512.json` | config 4 with 8192 / 512 frames per GPU (strong-scaling share at N=8; the reference's shipped batch) |")
 w(f"| `{tag}_bench_n2/4/8.json`, `{tag}_bench_strong_n*.json` | the same under `torch.distributed.run`, weak (65536 frames per GPU) and strong (65536 frames in total) scaling, where run |")
 w(f"| `{tag}_launches.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of one whole step (cold-cache, serialised: read the SHARES) |")
@@ -112,6 +113,10 @@ if c3:
 if c5 and n1:
     w("## BASELINE config 5 — near-coincident hands (every frame collides)\n")
     w(f"{c5['value']:,.0f} frames/s on one B200 ({c5['ms_per_step']:.0f} ms per 65536-frame step, e2e {c5['e2e']['value']:,.0f}): {n1['value'] / c5['value']:.2f}x slower than config 4.\n")
+    c58 = load("bench_cfg5_n8")
+    if c58:
+        w(f"On 8 B200 (65536 frames per GPU, `{tag}_bench_cfg5_n8.json`, `--steps 2 --e2e-steps 4`): **{c58['value']:,.0f}** frames/s "
+          f"({c58['ms_per_step']:.0f} ms per step) = {c58['value'] / (8 * c5['value']):.3f} of 8x the 1-GPU rate; e2e {c58['e2e']['value']:,.0f}.\n")
 if f8192 and f512 and n1:
     w("## Smaller batches per GPU (CUDA-graph replay of the stage calls)\n")
     w("| frames per GPU | frames/s | ms per step | per-frame rate vs 65536 frames |\n|---|---|---|---|")
