@@ -42,7 +42,7 @@ w(f"| `{tag}_ncu_summary.csv` | one row per stage x kernel of a steady-state ite
 w(f"| `{tag}_traffic.json`, `{tag}_issue.json` | DRAM bytes per launch unit and the issue-slot utilisation of `k_sdf_dir` from that capture (read by `bench.py`) |")
 w(f"| `{tag}_sdf_details.txt`, `{tag}_sdf_source_lines.txt` | `ncu --set full --import-source on` of the steady-state stage-2 launch of `k_sdf_dir`: details page, and stall samples / executed instructions per source line |")
 w(f"| `{tag}_sass_opcodes.csv` | SASS opcode histogram of every kernel of the library (`tools/sass_histogram.py`): UTCHMMA / LDTM / UTCBAR / UBLKCP / ... |")
-w("| `sanitizer/` | compute-sanitizer memcheck / racecheck / initcheck / synccheck over every kernel, regular and small-capacity library |\n")
+w("| `sanitizer/` | compute-sanitizer memcheck / racecheck / initcheck / synccheck over every kernel, regular and small-capacity library (0 errors; taken before the TMA-fed blend operand, the K split, the L2 prefetch and the children lists went in), and `sanitizer_final_racecheck/memcheck_default.log`: racecheck and memcheck of the FINAL build (0 hazards, 0 errors) |\n")
 
 if n1:
     sr, rf = n1["step_roofline"], n1["roofline"]
