@@ -47,6 +47,31 @@ def test_port_matches_unmodified_reference_live(model_root, oracle_layers):
         assert np.abs(got[k].astype(np.float64) - want[k]).max() <= 1e-6, k
 
 
+def test_log_values_match_the_reference_get_current_errors(model_root, oracle_layers):
+    """The GT-based log values of __compute_loss (optimize_model.py:276-306) that get_current_errors (:438-455) returns,
+    from the UNMODIFIED reference vs the port — with a frame whose GT has no right wrist (aligned to joint 21,
+    loss_utils.py:96-99) and one whose wrist weight falls between the two thresholds (not aligned at all).  The CUDA
+    model's get_current_errors is checked against the port on the GPU (test_current_errors_match_the_reference_log_values)."""
+    B = 3
+    data = H.make_batch(oracle_layers[0], 0, B, mode="collision")
+    data["joints_3d"] = np.array(data["joints_3d"])
+    data["joints_3d"][1, 0, 3] = 0.0
+    data["joints_3d"][2, 0, 3] = 0.3
+    batch = H.torch_batch(data)
+    ref = ref_shims.load_reference_model(ref_shims.make_opt(model_root, B, save_mid_freq=1), epochs=1)
+    ref.set_input(batch); ref.init_optimize(); ref.forward()
+    weights = ref.strategy[0]["loss_weights"]
+    getattr(ref, "_OptimizeModel__compute_loss")(weights)
+    want = ref.get_current_errors()
+    loop = H.oracle_loop(oracle_layers, B, 1, 1)
+    loop.set_input(batch); loop.init_optimize(); loop.forward(); loop.compute_loss(loop.strategy[0]["loss_weights"])
+    got = dict(joints_2d_loss=loop.joints_2d_loss, joints_3d_loss=loop.joints_3d_loss, hand_trans_loss=loop.hand_trans_loss,
+               collision_loss=loop.collision_loss, joints_3d_loss_p=loop.joints_3d_loss_p)
+    assert list(want) == list(got)
+    for k, v in want.items():
+        assert abs(float(got[k]) - float(v)) <= 1e-5 * max(abs(float(v)), 1e-6), (k, float(got[k]), float(v))
+
+
 def test_bs_norm_makes_a_shard_equal_to_the_full_batch(oracle_layers):
     """1/bs inside every mean interacts with Adam's eps: a shard must normalise by the full size."""
     data = H.make_batch(oracle_layers[0], 0, 2)
